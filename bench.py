@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Headline benchmark: Doppler-searched Msamples/s of the demodulator hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+
+A *step* is one chunk through the whole per-chunk path (chunk spectrum, Doppler search over all
+bins x masks, Doppler estimate, demod surface at the found bin, timing recovery, symbol decisions,
+result copy to the host).  ``value`` counts the NEW samples per chunk (Nfft - 2^overlap, the
+reference's own rate convention, pyCuSDR/demodulator_process.py:333) with the chunks already in HBM;
+``e2e`` is the same metric through the reference-facing Python class with host buffers (pinned H2D,
+D2H and the host-side stitching inside the timed region).
+
+Workload (BASELINE.json configs[1]): GMSK 9600 baud x 16 samples/symbol, 2^18-sample
+chunks, 256 Doppler bins, 8 matched filters, back-to-back benchmark packets with AWGN at "SNR" 12 dB, seed 2.
+
+N > 1 (torchrun, one rank per GPU): Doppler bins are sharded over the ranks, every rank holds the chunk,
+the [D, M] energy/peak tables are all-gathered with NCCL and every rank finishes the (cheap) estimate +
+demod redundantly -> strong scaling of the same workload.
+
+--impl reference: the reference has no CPU implementation of this path and its PyCUDA path cannot be
+installed offline, so this arm times the NumPy/SciPy oracle port (oracle/oracle.py) with all host cores.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config file, modulation, description)
+    "c1": ("CC11xx.json", None, "C1 CC11xx FSK-2 7416 baud x128, N=2^16, D=64, M=8"),
+    "c2": ("c2_base_2p18_256bins.json", "GMSK", "C2 GMSK 9600 baud x16, N=2^18, D=256, M=8"),
+    "c3": ("benchmark/bench_GMSK.json", "GMSK", "C3 bench_GMSK, N=2^15, D=64, M=8"),
+    "c4": ("c4_sband_2p20_4096bins.json", "GMSK", "C4 wide search, N=2^20, D=4096, M=8"),
+}
+RADIO = "UHF-H"
+
+
+def protocol_for(conf):
+    from pycusdr_b200.protocol import loadProtocol
+    return loadProtocol(conf["Main"]["protocols"]["UHF"])(conf=conf)
+
+
+def alg_counts(N, D, M, S):
+    """F_alg [FLOP] and B_alg / B_unfused [bytes] per chunk exactly as SURVEY.md 8(d) defines them."""
+    P = D * M * N
+    F = (D * M + M + 1.5) * 5 * N * math.log2(N) + 10 * P + 8 * M * N
+    B = 8 * N + 8 * M * N + 4 * D * M + 12 * S
+    return F, B, 32 * P
+
+
+def search_kernel_counts(N, D, M):
+    """Algorithmic work of the dominant kernel alone (the fused shift x filter -> inverse FFT -> |.|^2 ->
+    sum/arg-max): the D*M inverse transforms, the products and the |.|^2 accumulation of 8(d)'s F_alg, and its
+    compulsory bytes (chunk + filter spectra in, 12 bytes per (bin, mask) out)."""
+    P = D * M * N
+    return D * M * 5 * N * math.log2(N) + 10 * P, 8 * N + 8 * M * N + 12 * D * M
+
+
+def build_stream(conf, modulation, n_chunks, seed):
+    """Synthetic sample stream for ``n_chunks`` chunks (SURVEY 8(d) inputs)."""
+    from pycusdr_b200.benchmark import signals as S
+    cg = conf["GPU"]["UHF"]
+    cr = conf["Radios"]["Rx"][RADIO]
+    N, ovl = 2 ** cg["blockSize"], 2 ** cg["overlap"]
+    need = n_chunks * (N - ovl)
+    sps, baud = cr["samplesPerSym"], cr["baud"]
+    fs = sps * baud
+    rng = np.random.RandomState(seed)
+    if modulation is None:      # C1: FSK-2 packet, CC11xx style, Es/N0 15 dB
+        bits = S.createBitSequence(400, seed=123)
+        sig = S.modulateFSK(bits, sps)
+        one = np.concatenate((np.zeros(4096, np.complex64), sig, np.zeros(4096, np.complex64)))
+        f0 = cr["frequencyOffset_Hz"] + 7000.0
+        snr_r = 15 - 10 * np.log10(sps)
+    else:
+        one, _ = S.get_padded_packet(modulation, sps, fs, offset_freq=cr["frequencyOffset_Hz"])
+        one = one.astype(np.complex64)
+        f0 = None
+        snr_r = S.bench_snr_to_awgn_snr(modulation, 12.0, baud, fs)
+    reps = need // len(one) + 1
+    clean = np.tile(one, reps)[:need]
+    if f0 is not None:
+        clean = clean * np.exp(2j * np.pi * f0 / fs * np.arange(need)).astype(np.complex64)
+    p_sig = np.mean(np.abs(one) ** 2)
+    noise_p = p_sig * 10 ** (-snr_r / 10)
+    out = np.empty(need, dtype=np.complex64)
+    amp = np.float32(np.sqrt(noise_p / 2))
+    for a in range(0, need, 1 << 22):       # blockwise: keeps the float64 temporaries small
+        n = min(1 << 22, need - a)
+        out[a:a + n] = clean[a:a + n] + amp * (rng.randn(n) + 1j * rng.randn(n))
+    return out
+
+
+def chunks_from_stream(stream, N, ovl, n_chunks):
+    """[n_chunks, N] array: chunk c = overlap tail of chunk c-1 + new block c (demodulator_process.py:287,337)."""
+    step = N - ovl
+    out = np.zeros((n_chunks, N), dtype=np.complex64)
+    for c in range(n_chunks):
+        lo = c * step - ovl
+        if lo < 0:
+            out[c, ovl:] = stream[:step]
+        else:
+            out[c] = stream[lo:lo + N]
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:      # no NVML: report it instead of inventing clocks
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def oracle_baseline(conf, chunk, budget_s=20.0, workers=None):
+    """Times the NumPy/SciPy oracle (search + demod) on a bounded sample of one chunk.
+    This is the only place bench.py executes oracle/ code."""
+    from oracle import oracle as O
+    workers = workers or os.cpu_count()
+    orc = O.OracleDemodulator(conf, protocol_for(conf), RADIO, fft_workers=workers)
+    D = len(orc.doppCyperSymNorm)
+    X = O.forward_fft(chunk)
+    t0 = time.perf_counter()
+    O.search_energy(X, orc.masks, orc.doppCyperSymNorm[:4], orc.SUM_ALL_MASKS_PYTHON, workers=workers)
+    per_bin = (time.perf_counter() - t0) / 4
+    nb = int(max(4, min(D, budget_s / max(per_bin, 1e-6))))
+    shifts = orc.doppCyperSymNorm[:nb]
+    t0 = time.perf_counter()
+    X = O.forward_fft(chunk)
+    O.search_energy(X, orc.masks, shifts, orc.SUM_ALL_MASKS_PYTHON, workers=workers)
+    t_search = (time.perf_counter() - t0) * D / nb
+    orc.X = X
+    orc.dopplerIdxlast = int(orc.doppCyperSymNorm[D // 2])
+    t0 = time.perf_counter()
+    orc.demodulate()
+    t_demod = time.perf_counter() - t0
+    new_samples = orc.Nfft - orc.sigOverlap
+    return {"value": new_samples / (t_search + t_demod) / 1e6, "unit": "Msamples/s", "cores": int(workers),
+            "kind": "port",
+            "sample": f"one chunk: {nb} of {D} Doppler bins searched (scaled linearly to {D}) + full demod; "
+                      f"scipy.fft workers={workers}; {t_search + t_demod:.2f} s/chunk extrapolated"}
+
+
+def run_reference(args, conf, desc):
+    """--impl reference: NumPy/SciPy oracle port on the host cores, ``steps`` bounded samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cg = conf["GPU"]["UHF"]
+    N, ovl = 2 ** cg["blockSize"], 2 ** cg["overlap"]
+    stream = build_stream(conf, WORKLOADS[args.workload][1], 2, seed=2)
+    chunk = chunks_from_stream(stream, N, ovl, 2)[1]
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    budget = 60.0 / (steps + warm)
+    vals = []
+    for i in range(warm + steps):
+        r = oracle_baseline(conf, chunk, budget_s=budget)
+        if i >= warm:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "doppler_searched_msamples_per_s", "value": v, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": (N - ovl) / v / 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "note": "reference has no CPU path; NumPy/SciPy oracle port timed on host cores"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--log2-block", type=int, default=0)
+    args = ap.parse_args()
+
+    from pycusdr_b200.config import loadModularJson
+    cfg_file, modulation, desc = WORKLOADS[args.workload]
+    conf = loadModularJson(os.path.join(ROOT, "config", cfg_file))
+    if args.impl == "reference":
+        return run_reference(args, conf, desc)
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    conf["GPU"]["UHF"]["CUDA"]["device"] = local
+
+    from pycusdr_b200 import _native
+    from pycusdr_b200.demodulator import UHF
+    cg, cr = conf["GPU"]["UHF"], conf["Radios"]["Rx"][RADIO]
+    N, ovl = 2 ** cg["blockSize"], 2 ** cg["overlap"]
+    step_samples = N - ovl
+    fs = cr["baud"] * cr["samplesPerSym"]
+    protocol = protocol_for(conf)
+
+    # ---- workload: ring of distinct chunks larger than L2 ----
+    ring = max(8, min(128, (320 << 20) // (8 * N)))
+    stream = build_stream(conf, modulation, ring, seed=2)
+    host_chunks = chunks_from_stream(stream, N, ovl, ring)
+    dev_chunks = torch.from_numpy(host_chunks).cuda()
+    ring_bytes = dev_chunks.numel() * 8
+
+    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block)
+    eng = dem._engine
+    D, M = eng.D, eng.M
+    plan = eng.plan()
+    S_nom = N // cr["samplesPerSym"]
+
+    if world > 1:   # bin sharding: this rank searches rows [lo, hi)
+        per = (D + world - 1) // world
+        lo, hi = min(rank * per, D), min((rank + 1) * per, D)
+        eng.set_bin_range(lo, max(hi, lo + 1))
+        ts = torch.cuda.current_stream()
+        eng.set_stream(ts.cuda_stream)
+        pe, pv, po = eng.shard_buffers()
+
+        def as_tensor(ptr, dtype, typestr):
+            class _W:
+                __cuda_array_interface__ = {"shape": (D * M,), "typestr": typestr, "data": (ptr, False), "version": 2}
+            return torch.as_tensor(_W(), device=f"cuda:{local}")
+        tabs = [as_tensor(pe, torch.float32, "<f4"), as_tensor(pv, torch.float32, "<f4"), as_tensor(po, torch.int32, "<i4")]
+        even = (D % world == 0)
+        stage = [torch.empty(per * M, dtype=t.dtype, device=t.device) for t in tabs]
+        gath = [torch.empty(per * M * world, dtype=t.dtype, device=t.device) for t in tabs]
+
+        def one_step(ptr):
+            eng.upload_device(ptr)
+            eng.enqueue_search_local()
+            for t, s, g in zip(tabs, stage, gath):
+                s[:(hi - lo) * M].copy_(t[lo * M:hi * M])
+                dist.all_gather_into_tensor(g, s)
+                t.copy_(g[:D * M]) if even else [t[r * per * M:min((r + 1) * per, D) * M].copy_(
+                    g[r * per * M:r * per * M + (min((r + 1) * per, D) - r * per) * M]) for r in range(world)]
+            eng.enqueue_estimate_and_demod(True)
+            return eng.fetch()
+        timing_stream = ts
+    else:
+        def one_step(ptr):
+            eng.enqueue_device(ptr)
+            return eng.fetch()
+        timing_stream = torch.cuda.ExternalStream(eng.stream)
+
+    ptrs = [dev_chunks[i].data_ptr() for i in range(ring)]
+    checksum = 0
+    for i in range(args.warmup):
+        res, E, sym, centre, mag = one_step(ptrs[i % ring])
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.set_profiling(True)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(timing_stream)
+    for i in range(args.steps):
+        res, E, sym, centre, mag = one_step(ptrs[(args.warmup + i) % ring])
+        checksum += int(res.shift) + int(sym[:16].sum())
+    ev1.record(timing_stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    prof = eng.profile()
+    eng.set_profiling(False)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = step_samples / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e through the reference-facing class, host buffers ----
+    e2e_steps = args.e2e_steps or min(args.steps, 200)
+    e2e = None
+    if world == 1:
+        raw = dem.get_signalBufferHostPointer()
+        raw[:] = 0
+        blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
+        for c in range(min(5, ring)):
+            raw[ovl:] = blocks[c]
+            dem.uploadAndFindCarrier(raw)
+            dem.demodulate()
+            raw[:ovl] = raw[-ovl:]
+        torch.cuda.synchronize()
+        nbits = 0
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            raw[ovl:] = blocks[(5 + i) % ring]
+            dem.uploadAndFindCarrier(raw)
+            bits, centres, trust, spSym = dem.demodulate()
+            nbits += len(bits)
+            raw[:ovl] = raw[-ovl:]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        d2h = 88 + 4 * D * M + 12 * eng.max_sym + 2 * 8 * (max(int(res.sig_len), 0))
+        e2e = {"value": step_samples * e2e_steps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N,
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "bits_per_step": nbits / e2e_steps,
+               "api": "demodulator.UHF.Demodulator.uploadAndFindCarrier + demodulate (pinned chunk buffer)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (search) ----
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_file):
+        with open(peaks_file) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    fp32_peak = _native.measure_fp32_peak(local)
+    Dl = (eng.D if world == 1 else (hi - lo))
+    k_flop, k_bytes = search_kernel_counts(N, Dl, M)
+    F_alg, B_alg, B_unfused = alg_counts(N, D, M, S_nom)
+    s_ms, s_cnt = prof["search"]
+    search_ms = s_ms / max(s_cnt, 1)
+    roof = {
+        "bound": "fp32", "kernel": "search_os_kernel",
+        "achieved": k_flop / (search_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": k_flop / (search_ms * 1e-3) / 1e12 / fp32_peak,
+        "peak_source": "measured FMA loop on this GPU (pcs_measure_fp32_peak); nominal 74.4",
+        "kernel_ms": search_ms, "kernel_share_of_step": search_ms / ms_step,
+        "algorithmic_flop_per_launch": k_flop, "algorithmic_bytes_per_launch": k_bytes,
+        "hbm_fraction": k_bytes / (search_ms * 1e-3) / 1e9 / hbm_peak,
+        "surface_equiv_hbm_fraction": 32.0 * Dl * M * N / (search_ms * 1e-3) / 1e9 / hbm_peak,
+        "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+        "chunk_bound_ms": max(F_alg / (fp32_peak * 1e12), B_alg / (hbm_peak * 1e9)) * 1e3,
+        "chunk_frac": max(F_alg / (fp32_peak * 1e12), B_alg / (hbm_peak * 1e9)) * 1e3 / ms_step if world == 1 else None,
+        "traffic": None,
+    }
+    stages = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = oracle_baseline(conf, host_chunks[1], budget_s=15.0)
+
+    line = {
+        "metric": "doppler_searched_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "nfft": N, "overlap": ovl, "doppler_bins": D, "masks": M,
+                   "samples_per_step": step_samples, "x_real_time": value * 1e6 / fs,
+                   "path": {1: "overlap_save", 2: "full", 3: "parseval"}.get(plan["path"]),
+                   "block": 2 ** plan["log2_block"], "valid_per_block": plan["valid_per_block"],
+                   "l2": f"ring of {ring} distinct chunks = {ring_bytes >> 20} MiB (> 126 MiB L2), one per step",
+                   "parallelism": "single GPU" if world == 1 else f"doppler bins sharded over {world} GPUs + NCCL all-gather"},
+        "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
+        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

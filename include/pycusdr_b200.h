@@ -1,0 +1,192 @@
+/* pycusdr_b200 -- C ABI of the B200-native demodulator hot path.
+ *
+ * Drop-in boundary for pyCuSDR's per-chunk matched-filter Doppler search, symbol-timing recovery
+ * and symbol decisions.  The reference has no C ABI of its own: its demodulator class reaches the
+ * GPU through PyCUDA prepared kernels (pyCuSDR/demodulator/demodulator_base.py:353-390,505-506)
+ * and a ctypes binding to cuFFT (pyCuSDR/lib/cufft.py:143,231,266,283,365).  Each entry point below
+ * names the reference call sequence it replaces; the Python mirror of the reference class
+ * (pycusdr_b200/demodulator) binds them with ctypes, and INTEGRATION.md shows the stub a pyCuSDR
+ * maintainer would add.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative pcs_status;
+ * pcs_last_error() returns a thread-local message for the last failure.  One handle owns one CUDA
+ * stream, all device memory and one pinned host chunk buffer; calls on a handle must not overlap
+ * (the reference makes strictly alternating uploadAndFindCarrier/demodulate calls from one process,
+ * pyCuSDR/demodulator_process.py:293-297).  There is no CPU fallback: without a CUDA device
+ * pcs_create fails.
+ */
+#ifndef PYCUSDR_B200_H
+#define PYCUSDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCS_ABI_VERSION 1
+
+typedef enum {
+    PCS_OK = 0,
+    PCS_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    PCS_ERR_CUDA = -2,         /* CUDA runtime error (message in pcs_last_error) */
+    PCS_ERR_NO_DEVICE = -3,    /* no usable CUDA device */
+    PCS_ERR_STATE = -4         /* call order violated (e.g. demod before a chunk was uploaded) */
+} pcs_status;
+
+/* Which formulation computes the (bins x masks x samples) correlation surface. All give the same
+ * numbers to fp32 rounding (DESIGN.md "paths"):
+ *   AUTO          overlap-save when the filters' time support is short enough, else full length
+ *   OVERLAP_SAVE  blocks of B points, whole pipeline inside one SM's shared memory
+ *   FULL          Nfft-point inverse transforms (two tiled passes, L2-resident scratch)
+ *   PARSEVAL      energies only, no inverse transform (labelled variant, no peak / offsets)     */
+typedef enum { PCS_PATH_AUTO = 0, PCS_PATH_OVERLAP_SAVE = 1, PCS_PATH_FULL = 2, PCS_PATH_PARSEVAL = 3 } pcs_path;
+
+typedef struct {
+    int32_t abi_version;             /* PCS_ABI_VERSION */
+    int32_t device;                  /* conf['GPU'][..]['CUDA']['device']          dem_base:178 */
+    int32_t nfft;                    /* 2**blockSize                                dem_base:89,113 */
+    int32_t num_dopplers;            /* doppCarrierSteps                            dem_base:130 */
+    int32_t element_offset;          /* 1 when a noise row is prepended, else 0     dem_base:150-159 */
+    int32_t num_masks;               /* protocol.get_filter()[0]                    dem_base:196 */
+    int32_t window_width;            /* bitWindowWidth (WINDOW_WIDTH)               dem_base:116,412 */
+    int32_t sum_all_masks;           /* protocol.SUM_ALL_MASKS_PYTHON               dem_base:123-127,416 */
+    int32_t code_search_mask_offset; /* CODE_SEARCH_MASK_OFFSET                     dem_base:120,417 */
+    int32_t samples_per_sym;         /* samplesPerSym                               dem_base:103 */
+    int32_t path;                    /* pcs_path */
+    int32_t log2_block;              /* 0 = choose; else force the overlap-save block size 2**log2_block */
+    int32_t snr_window;              /* half width of the computeSNR windows (5)    dem_base:620 */
+    int32_t reserved[3];
+} pcs_config;
+
+/* Per-chunk scalar results (filled by pcs_search / pcs_demod / pcs_process). */
+typedef struct {
+    float best_idx;      /* findDopplerEst res[0]: weighted index of the two best bins  kern:562,590 */
+    float metric_db;     /* findDopplerEst res[1]                                       kern:565,592 */
+    int32_t low_idx;     /* int(best_idx)                                               dem_base:610 */
+    int32_t high_idx;    /* ceil(best_idx)                                              dem_base:611 */
+    int32_t shift;       /* dopplerIdxlast = round(interpolated spectrum shift)         dem_base:618 */
+    int32_t status;      /* 0 ok; 1 = NaN estimate (caller returns zeros)               dem_base:625-630 */
+    float timing[3];     /* findCodeRateAndPhase: index, atan2 phase, |.|^2             kern:306-310 */
+    int32_t n_sym;       /* number of symbol decisions = int(Nfft / spSym)              dem_base:999 */
+    double sp_sym;       /* Nfft / timing[0]                                            dem_base:735 */
+    double code_offset;  /* -phase/pi*spSym/2 (+ spSym-1 if negative)                   dem_base:745-747 */
+    float peak_val;      /* max |y|^2 over (bin, mask, timing offset) -- north-star peak */
+    int32_t peak_bin, peak_mask, peak_offset;
+    int32_t sig_start, sig_len, noise_start, noise_len; /* circular spectrum windows for computeSNR */
+    int32_t demod_shift; /* the shift the demod stage used */
+    int32_t pad_;
+} pcs_result;
+
+typedef struct pcs_handle pcs_handle;
+
+/* Replaces Demodulator.__init__'s device set-up (dem_base:177-221): context, mask upload
+ * (__uploadMaskToGPU :246-263), buffers (:433-498), FFT plans (:275-338,501), Doppler shift upload (:221).
+ * shifts: int32[num_dopplers + element_offset] = doppCyperSymNorm; masks: complex64[num_masks][nfft]
+ * (interleaved re,im) = conj(FFT(template)) exactly as protocol.get_filter returns them. */
+int pcs_create(const pcs_config* cfg, const int32_t* shifts, const float* masks, pcs_handle** out);
+
+/* Replaces Demodulator.__del__ (dem_base:517-533). */
+int pcs_destroy(pcs_handle* h);
+
+/* Replaces get_signalBufferHostPointer (dem_base:1055-1060): pinned complex64[nfft] owned by the
+ * handle; the caller writes samples in place. */
+void* pcs_host_buffer(pcs_handle* h);
+
+/* Replaces uploadToGPU (dem_base:548-558): asynchronous copy of the pinned chunk to HBM and the
+ * forward FFT.  Returns without synchronising. */
+int pcs_upload(pcs_handle* h);
+
+/* Same, but the chunk is already in HBM (device pointer to complex64[nfft]); no copy is made and the
+ * buffer must stay valid until the next synchronising call. */
+int pcs_upload_device(pcs_handle* h, const void* d_chunk);
+
+/* Replaces __findUHF's device part (dem_base:571-605): energy surface reduction, findDopplerEst,
+ * shift interpolation (:610-618).  Synchronises.  E_out (float32[(D+off)*M], reference layout) and
+ * res may be NULL. */
+int pcs_search(pcs_handle* h, pcs_result* res, float* E_out);
+
+/* Replaces __demodulate's device part (dem_base:776-803): surface at the selected shift, timing
+ * recovery, symbol decisions.  shift < 0 uses the shift found by the last search (kept on the
+ * device).  Synchronises.  sym/centre: int32[max_sym], mag: float32[max_sym]; the first res->n_sym
+ * entries are valid.  Any output pointer may be NULL. */
+int pcs_demod(pcs_handle* h, int32_t shift, pcs_result* res, int32_t* sym, int32_t* centre, float* mag);
+
+/* pcs_search followed by pcs_demod(shift = found) with a single synchronisation and no host round
+ * trip in between.  */
+int pcs_process(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag);
+
+/* Enqueue one whole chunk (search + demod) on a chunk already in HBM without synchronising; results
+ * are fetched later with pcs_fetch().  Used to keep several chunks in flight. */
+int pcs_enqueue_device(pcs_handle* h, const void* d_chunk);
+int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag);
+
+/* Upper bound of n_sym (= nfft / (samples_per_sym / 2), dem_base:468). */
+int32_t pcs_max_symbols(const pcs_handle* h);
+
+/* The two spectrum windows computeSNR averages (dem_base:653-661), gathered on the device:
+ * complex64[res.sig_len] starting at bin res.sig_start (circular) and the same for the noise window. */
+int pcs_snr_windows(pcs_handle* h, float* sig_win, float* noise_win);
+
+/* Inspection / parity hooks (synchronise; not on the hot path). */
+int pcs_get_spectrum(pcs_handle* h, float* X_out /* complex64[nfft] */);
+int pcs_get_peaks(pcs_handle* h, float* peak_val /* [D*M] */, int32_t* peak_offset /* [D*M] */);
+int pcs_get_demod_surface(pcs_handle* h, int32_t shift, float* y_out /* complex64[M*nfft] */);
+int pcs_get_demod_magnitudes(pcs_handle* h, float* ymag_out /* float32[M*nfft] */, float* p_out /* float32[nfft] */);
+
+/* Plan introspection: which path was chosen and its geometry. */
+typedef struct {
+    int32_t path;           /* pcs_path actually used */
+    int32_t log2_block;     /* overlap-save block size */
+    int32_t valid_per_block;
+    int32_t num_blocks;
+    int32_t support_pos;    /* filter time support: taps at n = 0..support_pos */
+    int32_t support_neg;    /* and at n = -support_neg..-1 */
+    int32_t groups_per_cta;
+    int32_t search_ctas;
+    int32_t search_smem_bytes;
+    int32_t sm_count;
+    int64_t device_bytes;   /* HBM allocated by the handle */
+} pcs_plan_info;
+int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info);
+
+/* Kernel launch counter (all launches issued through this handle since creation). */
+int64_t pcs_launch_count(const pcs_handle* h);
+
+/* CUDA stream the handle enqueues on (cudaStream_t as an integer), for event timing by the caller. */
+uint64_t pcs_stream(const pcs_handle* h);
+
+/* Doppler-bin sharding across GPUs (one process and one handle per GPU, every handle created with the
+ * FULL shift table).  Rank r restricts its search to rows [lo, hi) with pcs_set_bin_range, enqueues
+ * pcs_enqueue_search_local (search kernel + partial reduction, no estimate), all-gathers the row slices of
+ * the three tables returned by pcs_shard_buffers (float32[D*M] energies, float32[D*M] peak values,
+ * int32[D*M] peak offsets -- device pointers) with NCCL on the handle's stream, and then every rank runs
+ * pcs_enqueue_estimate_and_demod, which reproduces the single-GPU estimate bit for bit because it scans the
+ * same full table.  Results are collected with pcs_fetch. */
+int pcs_set_bin_range(pcs_handle* h, int32_t lo, int32_t hi);
+int pcs_shard_buffers(pcs_handle* h, void** d_energy, void** d_peak_val, void** d_peak_off);
+int pcs_enqueue_search_local(pcs_handle* h);
+int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod);
+
+/* Make the handle enqueue on a caller-owned stream (cudaStream_t as an integer), e.g. the framework
+ * stream NCCL collectives are ordered on.  The handle's own stream is destroyed. */
+int pcs_set_stream(pcs_handle* h, uint64_t stream);
+
+/* Per-stage device timing with CUDA events on the handle's stream (bench / roofline reporting).
+ * Stages: 0 chunk spectrum, 1 search kernel, 2 estimate, 3 demod surface, 4 timing + symbols,
+ * 5 partial reduction.  pcs_get_profile fills double[6] accumulated milliseconds and int64[6] counts. */
+#define PCS_NUM_STAGES 6
+int pcs_set_profiling(pcs_handle* h, int enable);
+int pcs_get_profile(pcs_handle* h, double* stage_ms, int64_t* stage_count);
+
+/* Measured fp32 FMA throughput of a device in TFLOP/s (the roofline denominator of the FFT-bound
+ * kernels; 16 independent FMA chains per thread, best of 4 timed launches). */
+int pcs_measure_fp32_peak(int device, double* tflops);
+
+const char* pcs_last_error(void);
+int pcs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCUSDR_B200_H */

@@ -1,0 +1,266 @@
+"""ctypes binding of libpycusdr_b200.so (include/pycusdr_b200.h).
+
+The library is built in-tree by ``pycusdr_b200/csrc/Makefile`` (or ``__graft_entry__.build()``).
+There is no CPU fallback: if the shared object is missing or no CUDA device is usable the
+caller gets an exception, never a silently slower path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpycusdr_b200.so")
+ABI_VERSION = 1
+
+PATH_AUTO, PATH_OVERLAP_SAVE, PATH_FULL, PATH_PARSEVAL = 0, 1, 2, 3
+
+
+class NativeError(RuntimeError):
+    """A pcs_* call failed; the message is pcs_last_error()."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"pycusdr_b200 native error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "device", "nfft", "num_dopplers", "element_offset", "num_masks", "window_width",
+        "sum_all_masks", "code_search_mask_offset", "samples_per_sym", "path", "log2_block", "snr_window")] + [
+        ("reserved", C.c_int32 * 3)]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("best_idx", C.c_float), ("metric_db", C.c_float), ("low_idx", C.c_int32), ("high_idx", C.c_int32),
+        ("shift", C.c_int32), ("status", C.c_int32), ("timing", C.c_float * 3), ("n_sym", C.c_int32),
+        ("sp_sym", C.c_double), ("code_offset", C.c_double), ("peak_val", C.c_float), ("peak_bin", C.c_int32),
+        ("peak_mask", C.c_int32), ("peak_offset", C.c_int32), ("sig_start", C.c_int32), ("sig_len", C.c_int32),
+        ("noise_start", C.c_int32), ("noise_len", C.c_int32), ("demod_shift", C.c_int32), ("pad_", C.c_int32)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "path", "log2_block", "valid_per_block", "num_blocks", "support_pos", "support_neg", "groups_per_cta",
+        "search_ctas", "search_smem_bytes", "sm_count")] + [("device_bytes", C.c_int64)]
+
+
+# every symbol include/pycusdr_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "pcs_create": (C.c_int, [C.POINTER(Config), _P, _P, C.POINTER(_P)]),
+    "pcs_destroy": (C.c_int, [_P]),
+    "pcs_host_buffer": (_P, [_P]),
+    "pcs_upload": (C.c_int, [_P]),
+    "pcs_upload_device": (C.c_int, [_P, _P]),
+    "pcs_search": (C.c_int, [_P, C.POINTER(Result), _P]),
+    "pcs_demod": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P]),
+    "pcs_process": (C.c_int, [_P, C.POINTER(Result), _P, _P, _P, _P]),
+    "pcs_enqueue_device": (C.c_int, [_P, _P]),
+    "pcs_fetch": (C.c_int, [_P, C.POINTER(Result), _P, _P, _P, _P]),
+    "pcs_max_symbols": (C.c_int32, [_P]),
+    "pcs_snr_windows": (C.c_int, [_P, _P, _P]),
+    "pcs_get_spectrum": (C.c_int, [_P, _P]),
+    "pcs_get_peaks": (C.c_int, [_P, _P, _P]),
+    "pcs_get_demod_surface": (C.c_int, [_P, C.c_int32, _P]),
+    "pcs_get_demod_magnitudes": (C.c_int, [_P, _P, _P]),
+    "pcs_get_plan": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "pcs_launch_count": (C.c_int64, [_P]),
+    "pcs_stream": (C.c_uint64, [_P]),
+    "pcs_set_bin_range": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "pcs_shard_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "pcs_enqueue_search_local": (C.c_int, [_P]),
+    "pcs_enqueue_estimate_and_demod": (C.c_int, [_P, C.c_int32]),
+    "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
+    "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
+    "pcs_get_profile": (C.c_int, [_P, _P, _P]),
+    "pcs_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "pcs_last_error": (C.c_char_p, []),
+    "pcs_abi_version": (C.c_int, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and type its entry points. Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `make -C pycusdr_b200/csrc` "
+                "(or __graft_entry__.build()); pycusdr_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.pcs_abi_version() != ABI_VERSION:
+            raise ImportError(f"ABI mismatch: library {lib.pcs_abi_version()}, binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def measure_fp32_peak(device=0):
+    """Measured fp32 FMA throughput of ``device`` in TFLOP/s."""
+    lib = load()
+    out = C.c_double(0)
+    rc = lib.pcs_measure_fp32_peak(int(device), C.byref(out))
+    if rc != 0:
+        raise NativeError(rc, lib.pcs_last_error().decode())
+    return out.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+class Engine:
+    """Thin object wrapper over one ``pcs_handle`` (one CUDA stream, one pinned chunk buffer)."""
+
+    def __init__(self, *, device, nfft, num_dopplers, element_offset, shifts, masks, window_width, sum_all_masks,
+                 code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5):
+        self.lib = load()
+        shifts = np.ascontiguousarray(shifts, dtype=np.int32)
+        masks = np.ascontiguousarray(masks, dtype=np.complex64)
+        if masks.ndim != 2 or masks.shape[1] != nfft:
+            raise ValueError(f"masks must have shape (num_masks, {nfft}), got {masks.shape}")
+        if shifts.shape != (num_dopplers + element_offset,):
+            raise ValueError("shifts must have num_dopplers + element_offset entries")
+        cfg = Config(ABI_VERSION, device, nfft, num_dopplers, element_offset, masks.shape[0], window_width,
+                     int(bool(sum_all_masks)), code_search_mask_offset, samples_per_sym, path, log2_block, snr_window)
+        self._h = _P()
+        self.nfft, self.D, self.M = nfft, num_dopplers + element_offset, masks.shape[0]
+        self._check(self.lib.pcs_create(C.byref(cfg), _ptr(shifts), _ptr(masks), C.byref(self._h)))
+        self.max_sym = self.lib.pcs_max_symbols(self._h)
+        buf = (C.c_float * (2 * nfft)).from_address(self.lib.pcs_host_buffer(self._h))
+        self.host_buffer = np.frombuffer(buf, dtype=np.complex64)
+        self._E = np.empty((self.D, self.M), dtype=np.float32)
+        self._sym = np.empty(self.max_sym, dtype=np.int32)
+        self._centre = np.empty(self.max_sym, dtype=np.int32)
+        self._mag = np.empty(self.max_sym, dtype=np.float32)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.host_buffer = None
+            self.lib.pcs_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- per chunk ------------------------------------------------------------------------------
+    def upload(self):
+        self._check(self.lib.pcs_upload(self._h))
+
+    def upload_device(self, dev_ptr):
+        self._check(self.lib.pcs_upload_device(self._h, _P(dev_ptr)))
+
+    def search(self):
+        res = Result()
+        self._check(self.lib.pcs_search(self._h, C.byref(res), _ptr(self._E)))
+        return res, self._E
+
+    def demod(self, shift=-1):
+        res = Result()
+        self._check(self.lib.pcs_demod(self._h, int(shift), C.byref(res), _ptr(self._sym), _ptr(self._centre),
+                                       _ptr(self._mag)))
+        n = res.n_sym
+        return res, self._sym[:n], self._centre[:n], self._mag[:n]
+
+    def process(self):
+        res = Result()
+        self._check(self.lib.pcs_process(self._h, C.byref(res), _ptr(self._E), _ptr(self._sym), _ptr(self._centre),
+                                         _ptr(self._mag)))
+        n = res.n_sym
+        return res, self._E, self._sym[:n], self._centre[:n], self._mag[:n]
+
+    def enqueue_device(self, dev_ptr):
+        self._check(self.lib.pcs_enqueue_device(self._h, _P(dev_ptr)))
+
+    def fetch(self):
+        res = Result()
+        self._check(self.lib.pcs_fetch(self._h, C.byref(res), _ptr(self._E), _ptr(self._sym), _ptr(self._centre),
+                                       _ptr(self._mag)))
+        n = res.n_sym
+        return res, self._E, self._sym[:n], self._centre[:n], self._mag[:n]
+
+    def snr_windows(self, res):
+        sig = np.empty(max(res.sig_len, 0), dtype=np.complex64)
+        noise = np.empty(max(res.noise_len, 0), dtype=np.complex64)
+        self._check(self.lib.pcs_snr_windows(self._h, _ptr(sig), _ptr(noise)))
+        return sig, noise
+
+    # -- inspection -----------------------------------------------------------------------------
+    def spectrum(self):
+        X = np.empty(self.nfft, dtype=np.complex64)
+        self._check(self.lib.pcs_get_spectrum(self._h, _ptr(X)))
+        return X
+
+    def peaks(self):
+        v = np.empty((self.D, self.M), dtype=np.float32)
+        o = np.empty((self.D, self.M), dtype=np.int32)
+        self._check(self.lib.pcs_get_peaks(self._h, _ptr(v), _ptr(o)))
+        return v, o
+
+    def demod_surface(self, shift):
+        y = np.empty((self.M, self.nfft), dtype=np.complex64)
+        self._check(self.lib.pcs_get_demod_surface(self._h, int(shift), _ptr(y)))
+        return y
+
+    def demod_magnitudes(self):
+        ymag = np.empty((self.M, self.nfft), dtype=np.float32)
+        p = np.empty(self.nfft, dtype=np.float32)
+        self._check(self.lib.pcs_get_demod_magnitudes(self._h, _ptr(ymag), _ptr(p)))
+        return ymag, p
+
+    def plan(self):
+        info = PlanInfo()
+        self._check(self.lib.pcs_get_plan(self._h, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in PlanInfo._fields_}
+
+    # -- bin sharding ----------------------------------------------------------------------------
+    def set_bin_range(self, lo, hi):
+        self._check(self.lib.pcs_set_bin_range(self._h, int(lo), int(hi)))
+
+    def shard_buffers(self):
+        """Device pointers of the [D*M] energy / peak-value / peak-offset tables."""
+        e, v, o = _P(), _P(), _P()
+        self._check(self.lib.pcs_shard_buffers(self._h, C.byref(e), C.byref(v), C.byref(o)))
+        return e.value, v.value, o.value
+
+    def enqueue_search_local(self):
+        self._check(self.lib.pcs_enqueue_search_local(self._h))
+
+    def enqueue_estimate_and_demod(self, with_demod=True):
+        self._check(self.lib.pcs_enqueue_estimate_and_demod(self._h, int(bool(with_demod))))
+
+    def set_stream(self, stream_ptr):
+        self._check(self.lib.pcs_set_stream(self._h, int(stream_ptr)))
+
+    STAGES = ("spectrum", "search", "estimate", "demod_surface", "timing_symbols", "reduce")
+
+    def set_profiling(self, enable=True):
+        self._check(self.lib.pcs_set_profiling(self._h, int(bool(enable))))
+
+    def profile(self):
+        """{stage: (total_ms, count)} accumulated since profiling was switched on."""
+        ms = np.zeros(len(self.STAGES), dtype=np.float64)
+        cnt = np.zeros(len(self.STAGES), dtype=np.int64)
+        self._check(self.lib.pcs_get_profile(self._h, _ptr(ms), _ptr(cnt)))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.STAGES)}
+
+    @property
+    def launch_count(self):
+        return self.lib.pcs_launch_count(self._h)
+
+    @property
+    def stream(self):
+        return self.lib.pcs_stream(self._h)

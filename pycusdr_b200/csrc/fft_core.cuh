@@ -1,0 +1,260 @@
+// In-SM Stockham FFT building blocks (sm_100a, complex fp32).
+//
+// One *group* of T = B/16 threads transforms B points that live in shared memory; every thread
+// owns 16 points in registers per pass, so a B = 16^P transform needs P passes and only P-1
+// shared-memory exchanges.  The first pass pulls its inputs through a caller-supplied functor
+// (global memory, a fused shift*mask product, ...) and the last pass hands its outputs to a
+// caller-supplied sink (shared memory, a fused |y|^2 / arg-max epilogue, ...), which is how the
+// Doppler-search kernels keep the correlation surface out of HBM.
+//
+// Pass structure (autosort, natural order in -> natural order out), current sub-length Ns:
+//   j in [0, B/R):  v[r] = in[j + r*B/R];  v[r] *= W_{Ns*R}^{(j mod Ns) * r};  V = DFT_R(v);
+//                   out[(j div Ns)*Ns*R + (j mod Ns) + q*Ns] = V[q]
+// Shared buffers are indexed through PADI() (one float2 of padding every 16) which makes both
+// the strided stores of the early passes and the unit-stride loads conflict-free for 64-bit
+// accesses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pcs {
+
+#define PCS_DEVINL __device__ __forceinline__
+
+PCS_DEVINL int padi(int i) { return i + (i >> 4); }
+constexpr int padded_len(int n) { return n + (n >> 4); }
+
+PCS_DEVINL float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PCS_DEVINL float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PCS_DEVINL float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+PCS_DEVINL float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// |z|^2 with the contraction nvcc applies to the reference's ComplexAbsSquared (FMUL + FFMA).
+PCS_DEVINL float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+// multiply by exp(i*DIR*theta) given c = cos(theta), s = sin(theta)
+template <int DIR>
+PCS_DEVINL float2 mulw(float2 v, float c, float s) {
+    if (DIR < 0) return make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
+    return make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.y, c, v.x * s));
+}
+// multiply by DIR*i
+template <int DIR>
+PCS_DEVINL float2 muli(float2 v) {
+    return DIR < 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
+}
+
+PCS_DEVINL void dft2(float2& a, float2& b) {
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+template <int DIR>
+PCS_DEVINL void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = muli<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+#define PCS_SQRT1_2 0.70710678118654752440f
+#define PCS_COS_PI_8 0.92387953251128675613f
+#define PCS_SIN_PI_8 0.38268343236508977173f
+
+// In-register DFT of R points.  Output V[q] is left in register slot OutSlot<R>::of(q)... the
+// inverse map (slot -> q) is what the callers need and is given by dft_q<R>(slot).
+template <int R>
+__host__ __device__ constexpr int dft_q(int slot) {
+    return R == 16 ? ((slot >> 2) + ((slot & 3) << 2)) : R == 8 ? ((slot >> 2) + ((slot & 3) << 1)) : slot;
+}
+
+template <int R, int DIR>
+struct Dft;
+
+template <int DIR>
+struct Dft<2, DIR> {
+    static PCS_DEVINL void run(float2* v) { dft2(v[0], v[1]); }
+};
+template <int DIR>
+struct Dft<4, DIR> {
+    static PCS_DEVINL void run(float2* v) { dft4<DIR>(v[0], v[1], v[2], v[3]); }
+};
+template <int DIR>
+struct Dft<8, DIR> {
+    // r = r1*4 + r2 (R1 = 2, R2 = 4); V[q1 + 2*q2] ends in slot 4*q1 + q2
+    static PCS_DEVINL void run(float2* v) {
+#pragma unroll
+        for (int r2 = 0; r2 < 4; ++r2) dft2(v[r2], v[4 + r2]);
+        // slot 4 + r2 *= W8^{r2}
+        {
+            float2 t = v[5];  // W8^1 = (1 + DIR*i)/sqrt2
+            v[5] = DIR < 0 ? make_float2((t.x + t.y) * PCS_SQRT1_2, (t.y - t.x) * PCS_SQRT1_2)
+                           : make_float2((t.x - t.y) * PCS_SQRT1_2, (t.y + t.x) * PCS_SQRT1_2);
+            v[6] = muli<DIR>(v[6]);  // W8^2 = DIR*i
+            t = v[7];                // W8^3 = (-1 + DIR*i)/sqrt2
+            v[7] = DIR < 0 ? make_float2((t.y - t.x) * PCS_SQRT1_2, (-t.x - t.y) * PCS_SQRT1_2)
+                           : make_float2((-t.x - t.y) * PCS_SQRT1_2, (t.x - t.y) * PCS_SQRT1_2);
+        }
+        dft4<DIR>(v[0], v[1], v[2], v[3]);
+        dft4<DIR>(v[4], v[5], v[6], v[7]);
+    }
+};
+template <int DIR>
+struct Dft<16, DIR> {
+    // r = r1*4 + r2 (R1 = R2 = 4); V[q1 + 4*q2] ends in slot 4*q1 + q2
+    static PCS_DEVINL void run(float2* v) {
+#pragma unroll
+        for (int r2 = 0; r2 < 4; ++r2) dft4<DIR>(v[r2], v[4 + r2], v[8 + r2], v[12 + r2]);
+        // slot 4*q1 + r2 *= W16^{q1*r2}
+        v[5] = mulw<DIR>(v[5], PCS_COS_PI_8, PCS_SIN_PI_8);     // W16^1
+        v[6] = mulw<DIR>(v[6], PCS_SQRT1_2, PCS_SQRT1_2);       // W16^2
+        v[7] = mulw<DIR>(v[7], PCS_SIN_PI_8, PCS_COS_PI_8);     // W16^3
+        v[9] = mulw<DIR>(v[9], PCS_SQRT1_2, PCS_SQRT1_2);       // W16^2
+        v[10] = muli<DIR>(v[10]);                               // W16^4
+        v[11] = mulw<DIR>(v[11], -PCS_SQRT1_2, PCS_SQRT1_2);    // W16^6
+        v[13] = mulw<DIR>(v[13], PCS_SIN_PI_8, PCS_COS_PI_8);   // W16^3
+        v[14] = mulw<DIR>(v[14], -PCS_SQRT1_2, PCS_SQRT1_2);    // W16^6
+        v[15] = mulw<DIR>(v[15], -PCS_COS_PI_8, -PCS_SIN_PI_8); // W16^9
+#pragma unroll
+        for (int q1 = 0; q1 < 4; ++q1) dft4<DIR>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+    }
+};
+
+// v[r] *= w^r for r = 1..R-1, powers built by multiplication with depth <= 4.
+template <int R>
+PCS_DEVINL void apply_twiddle_powers(float2* v, float2 w1) {
+    if (R == 2) {
+        v[1] = cmul(v[1], w1);
+        return;
+    }
+    float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
+    if (R >= 8) {
+        float2 w4 = cmul(w2, w2);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+        if (R >= 16) {
+            float2 w8 = cmul(w4, w4);
+            v[8] = cmul(v[8], w8);
+            v[9] = cmul(v[9], cmul(w8, w1));
+            v[10] = cmul(v[10], cmul(w8, w2));
+            v[11] = cmul(v[11], cmul(w8, w3));
+            float2 w12 = cmul(w8, w4);
+            v[12] = cmul(v[12], w12);
+            v[13] = cmul(v[13], cmul(w12, w1));
+            v[14] = cmul(v[14], cmul(w12, w2));
+            v[15] = cmul(v[15], cmul(w12, w3));
+        }
+    }
+}
+
+// exp(-2*pi*i * num / den) for 0 <= num < den <= 2^24 (exact argument reduction in fp32).
+PCS_DEVINL float2 unit_phasor_neg(uint32_t num, float inv_den) {
+    float s, c;
+    sincospif(-2.0f * ((float)num * inv_den), &s, &c);
+    return make_float2(c, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Group barrier: T threads of one group (T multiple of 32); id in 1..15 (0 is __syncthreads).
+// ---------------------------------------------------------------------------------------------
+template <int T>
+PCS_DEVINL void group_sync(int bar_id) {
+    if (T <= 32) {
+        __syncwarp();   // groups of <= 32 threads live inside one warp and run convergent code
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(T) : "memory");
+    }
+}
+
+template <int LOGB>
+struct FftShape {
+    static constexpr int B = 1 << LOGB;
+    static constexpr int T = B / 16;                    // threads per group
+    static constexpr int NPASS = (LOGB + 3) / 4;
+    static constexpr int LOG_RLAST = LOGB - 4 * (NPASS - 1);
+    static constexpr int RLAST = 1 << LOG_RLAST;
+    static constexpr int WORK = padded_len(B);          // float2 per work buffer
+};
+
+struct NoPre {
+    PCS_DEVINL void operator()(float2*, int) const {}
+};
+
+// One pass. R = radix, LOGNS = log2(Ns).  in: idx -> float2.  out: (idx, float2, slot) where slot is
+// the compile-time register slot (0..15) of that output inside the thread.  pre(v, j) may modify the
+// freshly loaded radix-R vector of butterfly j (used to fuse the Doppler rotation into pass 0).
+template <int LOGB, int R, int LOGNS, int DIR, typename In, typename Out, typename Pre = NoPre>
+PCS_DEVINL void fft_pass(int t, const float2* __restrict__ tw, In in, Out out, Pre pre = Pre()) {
+    constexpr int B = 1 << LOGB, T = B / 16, NB = 16 / R, STR = B / R, NS = 1 << LOGNS;
+    constexpr int LOGR = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+    float2 v[NB][R];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = t + b * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[b][r] = in(j + r * STR);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = t + b * T;
+        const int k = j & (NS - 1);
+        pre(v[b], j);
+        if (LOGNS > 0) {
+            float2 w1 = __ldg(&tw[k * (B / (NS * R))]);   // forward table exp(-2 pi i t / B)
+            if (DIR > 0) w1 = cconj(w1);
+            apply_twiddle_powers<R>(v[b], w1);
+        }
+        Dft<R, DIR>::run(v[b]);
+        const int j0 = ((j >> LOGNS) << (LOGNS + LOGR)) + k;
+#pragma unroll
+        for (int s = 0; s < R; ++s) out(j0 + dft_q<R>(s) * NS, v[b][s], b * R + s);
+    }
+}
+
+// Whole transform for one group.  ``work0``/``work1`` are the group's private shared buffers of
+// FftShape<LOGB>::WORK float2 each.  Pass p stores to work[p & 1] and pass p+1 loads from it, so
+// NPASS-1 barriers are enough inside one transform; back-to-back transforms on the same buffers
+// are safe for odd NPASS, and one trailing barrier is added for even NPASS (the last pass then
+// still reads work0 while the next transform's pass 0 would overwrite it).
+// src(idx) supplies natural-order input idx, sink(idx, val, slot) receives natural-order output idx.
+template <int LOGB, int DIR, typename Src, typename Sink, typename Pre = NoPre>
+PCS_DEVINL void group_fft(float2* work0, float2* work1, const float2* __restrict__ tw, int t, int bar_id,
+                          Src src, Sink sink, Pre pre = Pre()) {
+    using S = FftShape<LOGB>;
+    auto ld0 = [&](int i) { return work0[padi(i)]; };
+    auto ld1 = [&](int i) { return work1[padi(i)]; };
+    auto st0 = [&](int i, float2 v, int) { work0[padi(i)] = v; };
+    auto st1 = [&](int i, float2 v, int) { work1[padi(i)] = v; };
+    static_assert(S::NPASS >= 2 && S::NPASS <= 4, "supported transform sizes: 2^5 .. 2^16");
+    if constexpr (S::NPASS == 2) {
+        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, S::RLAST, 4, DIR>(t, tw, ld0, sink);
+        group_sync<S::T>(bar_id);
+    } else if constexpr (S::NPASS == 3) {
+        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, 16, 4, DIR>(t, tw, ld0, st1);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, S::RLAST, 8, DIR>(t, tw, ld1, sink);
+    } else {
+        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, 16, 4, DIR>(t, tw, ld0, st1);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, 16, 8, DIR>(t, tw, ld1, st0);
+        group_sync<S::T>(bar_id);
+        fft_pass<LOGB, S::RLAST, 12, DIR>(t, tw, ld0, sink);
+        group_sync<S::T>(bar_id);
+    }
+}
+
+}  // namespace pcs

@@ -1,0 +1,605 @@
+// Device kernels of the demodulator hot path (sm_100a).  See DESIGN.md for the data layout and
+// the per-kernel roofline; reference line numbers refer to /root/reference/pyCuSDR/demodulator/
+// cuda_kernels.cu ("kern") and demodulator_base.py ("dem_base").
+#pragma once
+#include <math_constants.h>
+#include "fft_core.cuh"
+
+namespace pcs {
+
+// ---------------------------------------------------------------------------------------------
+// Result block written by the device and copied to pinned host memory once per chunk.
+// ---------------------------------------------------------------------------------------------
+#define PCS_WINDOW_MAX 8192
+#define PCS_NUM_STAGES 6
+enum { PCS_STAGE_SPECTRUM = 0, PCS_STAGE_SEARCH = 1, PCS_STAGE_ESTIMATE = 2, PCS_STAGE_DEMOD_SURFACE = 3,
+       PCS_STAGE_TIMING_SYMBOLS = 4, PCS_STAGE_REDUCE = 5 };
+struct DevResult {
+    float best_idx;      // findDopplerEst res[0]  (kern:562,590)
+    float metric_db;     // findDopplerEst res[1]  (kern:565,592)
+    int low_idx;         // int(best)              (dem_base:610)
+    int high_idx;        // ceil(best)             (dem_base:611)
+    int shift;           // dopplerIdxlast         (dem_base:618)
+    int status;          // 0 ok, 1 = NaN estimate (dem_base:625-630)
+    float timing[3];     // findCodeRateAndPhase out[0..2] (kern:306-310)
+    int n_sym;           // int(Nfft / spSym)      (dem_base:999)
+    double sp_sym;       // dem_base:735
+    double code_offset;  // dem_base:745-747
+    float peak_val;      // north-star peak: max |y|^2 over (bin, mask, offset)
+    int peak_bin, peak_mask, peak_offset;
+    int sig_start, sig_len, noise_start, noise_len;   // circular windows of X gathered for computeSNR
+    int demod_shift;     // shift actually used by the demod stage
+    int pad_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// a6 + a7 + a8 fused (overlap-save form): for one (Doppler bin d, block b) a group
+//   1. loads B chunk samples, rotates them by exp(-2 pi i s_d n / N)  (== spectrum shift by s_d,
+//      kern:370) and runs a B-point forward FFT into shared memory,
+//   2. for every mask m multiplies by the B-point conjugate filter spectrum (== Mk[m, k*N/B],
+//      pre-scaled by N/B) and runs the inverse FFT,
+//   3. reduces sum |y|^2 (kern:442-443, the 2^-18 scale is applied by the reduce kernel) and the
+//      running max / arg-max over the block's valid outputs straight from registers.
+// Only 12 bytes per (d, m, block) leave the SM.
+// ---------------------------------------------------------------------------------------------
+struct OsSearchParams {
+    const float2* __restrict__ x;       // [N] chunk in HBM
+    const float2* __restrict__ gb;      // [M][B] filter spectra, scaled by N/B
+    const float2* __restrict__ tw;      // [B] exp(-2 pi i t / B)
+    const int* __restrict__ shifts;     // [D]
+    float* __restrict__ psum;           // [D][M][nblk]
+    float* __restrict__ pmax;           // [D][M][nblk]
+    int* __restrict__ pidx;             // [D][M][nblk]
+    int N, D, M, nblk, V, Lpos;
+    float invN;
+};
+
+struct PeakAcc {
+    float sum, best;
+    int idx;
+    PCS_DEVINL void init() {
+        sum = 0.f;
+        best = -1.f;
+        idx = 0x7fffffff;
+    }
+    PCS_DEVINL void take(float mag, int n) {
+        sum += mag;
+        if (mag > best || (mag == best && n < idx)) {
+            best = mag;
+            idx = n;
+        }
+    }
+    PCS_DEVINL void merge(float ob, int oi) {
+        if (ob > best || (ob == best && oi < idx)) {
+            best = ob;
+            idx = oi;
+        }
+    }
+    PCS_DEVINL void warp_reduce() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            merge(ob, oi);
+        }
+    }
+};
+
+// Doppler rotation fused into pass 0 of the forward transform: v[r] *= base * step^r.
+struct RotatePre {
+    float2 step;
+    uint32_t shift, n_first, nmask;
+    float invN;
+    PCS_DEVINL void operator()(float2* v, int j) const {
+        const uint32_t n = (n_first + (uint32_t)j) & nmask;
+        const float2 base = unit_phasor_neg((shift * n) & nmask, invN);
+        apply_twiddle_powers<16>(v, step);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], base);
+    }
+};
+
+template <int LOGB, int G>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSearchParams p) {
+    using S = FftShape<LOGB>;
+    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* smem = reinterpret_cast<float2*>(smem_raw);
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = smem + (size_t)g * 3 * S::WORK;
+    float2* work0 = xb + S::WORK;
+    float2* work1 = work0 + S::WORK;
+    // per-group reduction scratch behind the FFT buffers: [G][M][NW] x {sum, max, idx}
+    float* red = reinterpret_cast<float*>(smem + (size_t)G * 3 * S::WORK) + (size_t)g * p.M * NW * 3;
+    const int bar_id = 1 + g;
+
+    const long long item = (long long)blockIdx.x * G + g;
+    if (item >= (long long)p.nblk * p.D) return;      // whole group leaves (own barrier id)
+    const int blk = (int)(item / p.D), d = (int)(item % p.D);
+    const uint32_t nmask = (uint32_t)p.N - 1u;
+    const uint32_t shift = (uint32_t)p.shifts[d];
+    const int n0 = blk * p.V;
+    const uint32_t n_first = (uint32_t)(n0 - p.Lpos) & nmask;
+
+    // ---- forward transform of the rotated block -> xb (natural order) ----
+    {
+        RotatePre pre;
+        pre.shift = shift;
+        pre.n_first = n_first;
+        pre.nmask = nmask;
+        pre.invN = p.invN;
+        pre.step = unit_phasor_neg((shift * (uint32_t)(B / 16)) & nmask, p.invN);
+        auto src = [&](int i) { return __ldg(&p.x[(n_first + (uint32_t)i) & nmask]); };
+        auto sink = [&](int i, float2 v, int) { xb[padi(i)] = v; };
+        group_fft<LOGB, -1>(work0, work1, p.tw, t, bar_id, src, sink, pre);
+    }
+    group_sync<T>(bar_id);
+
+    const int vlen = min(p.V, p.N - n0);
+    const int lane = t & 31, warp = t >> 5;
+    for (int m = 0; m < p.M; ++m) {
+        const float2* __restrict__ gm = p.gb + (size_t)m * B;
+        PeakAcc acc;
+        acc.init();
+        auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
+        auto sink = [&](int i, float2 v, int) {
+            const int rel = i - p.Lpos;
+            if (rel >= 0 && rel < vlen) acc.take(cabs2(v), n0 + rel);
+        };
+        group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
+        acc.warp_reduce();
+        if (lane == 0) {
+            float* r = red + ((size_t)m * NW + warp) * 3;
+            r[0] = acc.sum;
+            r[1] = acc.best;
+            r[2] = __int_as_float(acc.idx);
+        }
+    }
+    group_sync<T>(bar_id);
+    for (int m = t; m < p.M; m += T) {
+        PeakAcc acc;
+        acc.init();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float* r = red + ((size_t)m * NW + w) * 3;
+            acc.sum += r[0];
+            acc.merge(r[1], __float_as_int(r[2]));
+        }
+        const size_t o = ((size_t)d * p.M + m) * p.nblk + blk;
+        p.psum[o] = acc.sum;
+        p.pmax[o] = acc.best;
+        p.pidx[o] = acc.idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reduce the per-block partials (fixed order -> bit-reproducible, unlike the reference's float
+// atomics, kern:463,474).  One warp per (d, m).
+// ---------------------------------------------------------------------------------------------
+__global__ void search_reduce_kernel(const float* __restrict__ psum, const float* __restrict__ pmax,
+                                     const int* __restrict__ pidx, int DM, int nblk, float* __restrict__ Efull,
+                                     float* __restrict__ peak_val, int* __restrict__ peak_off) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= DM) return;
+    PeakAcc acc;
+    acc.init();
+    const size_t base = (size_t)w * nblk;
+    for (int b = lane; b < nblk; b += 32) {
+        acc.sum += psum[base + b];
+        acc.merge(pmax[base + b], pidx[base + b]);
+    }
+    acc.warp_reduce();
+    if (lane == 0) {
+        Efull[w] = acc.sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
+        peak_val[w] = acc.best;
+        peak_off[w] = acc.idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9 findDopplerEst (kern:502-597) + the host interpolation of dem_base:610-618 done on the
+// device in float64 so that the demod stage can be enqueued without a host round trip, + the
+// north-star peak, + the spectrum windows computeSNR needs (dem_base:635-667).
+// Single CTA.
+// ---------------------------------------------------------------------------------------------
+struct EstimateParams {
+    const float* __restrict__ Efull;    // [D][M] per-mask energies
+    float* __restrict__ E;              // [D][M] reference layout (SUM mode: column 0 only)
+    const float* __restrict__ peak_val; // [D][M]
+    const int* __restrict__ peak_off;   // [D][M]
+    const int* __restrict__ shifts;     // [D]
+    const float2* __restrict__ X;       // [N] chunk spectrum (may be null -> no windows)
+    float2* __restrict__ sig_win;       // [PCS_WINDOW_MAX]
+    float2* __restrict__ noise_win;     // [PCS_WINDOW_MAX]
+    DevResult* __restrict__ res;
+    int D, M, N, num_dopplers, element_offset, sum_all, window_width;
+};
+
+__global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
+    __shared__ float s_idx[32], s_val[32];
+    __shared__ float s_pk[256];
+    __shared__ int s_pki[256];
+    const int tid = threadIdx.x;
+    // 1. reference layout of E
+    for (int d = tid; d < p.D; d += blockDim.x) {
+        if (p.sum_all) {
+            float acc = p.Efull[(size_t)d * p.M];
+            for (int m = 1; m < p.M; ++m) acc += p.Efull[(size_t)d * p.M + m];   // kern:459-462
+            p.E[(size_t)d * p.M] = acc;
+            for (int m = 1; m < p.M; ++m) p.E[(size_t)d * p.M + m] = 0.f;
+        } else {
+            for (int m = 0; m < p.M; ++m) p.E[(size_t)d * p.M + m] = p.Efull[(size_t)d * p.M + m];
+        }
+    }
+    __syncthreads();
+    // 2. per-column running top-2 (kern:527-544), one thread per column
+    const int ncols = p.sum_all ? 1 : p.M;
+    if (tid < ncols) {
+        float v0 = 0.f, v1 = 0.f;
+        int i0 = 0, i1 = 0, cur = 0;
+        for (int i = p.element_offset; i < p.num_dopplers + p.element_offset; ++i) {
+            const float e = p.E[(size_t)i * p.M + tid];
+            if (e > (cur ? v1 : v0)) {
+                if (cur) { v1 = e; i1 = i; } else { v0 = e; i0 = i; }
+                cur = (v0 >= v1) ? 1 : 0;
+            }
+        }
+        const float tmp = __fmaf_rn((float)i0, v0, __fmul_rn((float)i1, v1));   // SASS: FMUL + FFMA
+        float bl = __fdiv_rn(tmp, __fadd_rn(v0, v1));
+        float vl = __fdiv_rn(tmp, (float)(i0 + i1));
+        if (p.element_offset > 0) vl = __fdiv_rn(cur ? v0 : v1, p.E[tid]);    // kern:550-554
+        s_idx[tid] = bl;
+        s_val[tid] = vl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float best, metric;
+        if (p.sum_all) {
+            best = s_idx[0];
+            metric = s_val[0];
+        } else {
+            // mean over masks (xor-butterfly order for power-of-two M, kern:576-580)
+            float a[32], b[32];
+            for (int m = 0; m < p.M; ++m) { a[m] = s_idx[m]; b[m] = s_val[m]; }
+            if ((p.M & (p.M - 1)) == 0) {
+                for (int step = p.M >> 1; step > 0; step >>= 1)
+                    for (int m = 0; m < step; ++m) { a[m] = a[m] + a[m ^ step]; b[m] = b[m] + b[m ^ step]; }
+            } else {
+                for (int m = 1; m < p.M; ++m) { a[0] += a[m]; b[0] += b[m]; }
+            }
+            best = a[0] / (float)p.M;
+            metric = b[0] / (float)p.M;
+        }
+        DevResult* r = p.res;
+        r->best_idx = best;
+        r->metric_db = 10.f * log10f(metric);
+        // host interpolation, float64 (dem_base:610-618)
+        if (isnan(best) || best < 0.f || best > (float)(p.D - 1)) {
+            r->status = 1;
+            r->low_idx = r->high_idx = 0;
+            r->shift = 0;
+        } else {
+            const double b = (double)best;
+            const int lo = (int)b, hi = (int)ceil(b);
+            const double frac = fmod(b, 1.0);
+            const int slo = p.shifts[lo], shi = p.shifts[hi];
+            r->status = 0;
+            r->low_idx = lo;
+            r->high_idx = hi;
+            r->shift = (int)rint((double)slo + (double)(shi - slo) * frac);   // np.round: half to even
+        }
+    }
+    // 3. north-star peak over (bin, mask): lowest flat index wins ties
+    {
+        float bv = -1.f;
+        int bi = 0x7fffffff;
+        const int first = p.element_offset * p.M, last = (p.element_offset + p.num_dopplers) * p.M;
+        for (int i = first + tid; i < last; i += blockDim.x) {
+            const float v = p.peak_val[i];
+            if (v > bv) { bv = v; bi = i; }
+        }
+        s_pk[tid] = bv;
+        s_pki[tid] = bi;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (tid < s) {
+                const float ov = s_pk[tid + s];
+                const int oi = s_pki[tid + s];
+                if (ov > s_pk[tid] || (ov == s_pk[tid] && oi < s_pki[tid])) { s_pk[tid] = ov; s_pki[tid] = oi; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int i = s_pki[0];
+            p.res->peak_val = s_pk[0];
+            p.res->peak_bin = i / p.M;
+            p.res->peak_mask = i % p.M;
+            p.res->peak_offset = p.peak_off[i];
+        }
+    }
+    __syncthreads();
+    // 4. spectrum windows for computeSNR: circular [s_lo - w, s_hi + w) and the same + N/2
+    if (p.X != nullptr) {
+        const DevResult* r = p.res;
+        int sig_start = 0, len = 0;
+        if (r->status == 0) {
+            const int slo = p.shifts[r->low_idx], shi = p.shifts[r->high_idx];
+            const int nmask = p.N - 1;
+            sig_start = (slo - p.window_width) & nmask;
+            len = ((shi - slo) & nmask) + 2 * p.window_width;
+            if (len > PCS_WINDOW_MAX) len = 0;      // host falls back to a full spectrum read
+            const int noise_start = (sig_start + p.N / 2) & nmask;
+            for (int i = tid; i < len; i += blockDim.x) {
+                p.sig_win[i] = p.X[(sig_start + i) & nmask];
+                p.noise_win[i] = p.X[(noise_start + i) & nmask];
+            }
+            if (tid == 0) {
+                p.res->sig_start = sig_start;
+                p.res->sig_len = len;
+                p.res->noise_start = noise_start;
+                p.res->noise_len = len;
+            }
+        } else if (tid == 0) {
+            p.res->sig_start = p.res->sig_len = p.res->noise_start = p.res->noise_len = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12 + a13 (first half) fused, overlap-save form: y[m, n] at the selected shift for all masks;
+// writes |y|^2 (what findCentres consumes, kern:111,129) and p[n] = sum_m |y|^2 (kern:191-205);
+// optionally the complex surface for inspection.  The shift comes from device memory.
+// ---------------------------------------------------------------------------------------------
+struct OsDemodParams {
+    const float2* __restrict__ x;
+    const float2* __restrict__ gb;
+    const float2* __restrict__ tw;
+    const DevResult* __restrict__ res;   // shift source when shift_override < 0
+    float* __restrict__ ymag;            // [M][N]
+    float* __restrict__ p;               // [N]
+    float2* __restrict__ ycplx;          // [M][N] or null
+    int N, M, nblk, V, Lpos, shift_override, mask_lo, mask_hi;
+    float invN;
+};
+
+template <int LOGB, int G>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T) demod_os_kernel(OsDemodParams p) {
+    using S = FftShape<LOGB>;
+    constexpr int B = S::B, T = S::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* smem = reinterpret_cast<float2*>(smem_raw);
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = smem + (size_t)g * 3 * S::WORK;
+    float2* work0 = xb + S::WORK;
+    float2* work1 = work0 + S::WORK;
+    const int bar_id = 1 + g;
+    const int blk = blockIdx.x * G + g;
+    if (blk >= p.nblk) return;
+    const uint32_t nmask = (uint32_t)p.N - 1u;
+    const uint32_t shift = (uint32_t)(p.shift_override >= 0 ? p.shift_override : p.res->shift) & nmask;
+    const int n0 = blk * p.V;
+    const uint32_t n_first = (uint32_t)(n0 - p.Lpos) & nmask;
+    {
+        RotatePre pre;
+        pre.shift = shift;
+        pre.n_first = n_first;
+        pre.nmask = nmask;
+        pre.invN = p.invN;
+        pre.step = unit_phasor_neg((shift * (uint32_t)(B / 16)) & nmask, p.invN);
+        auto src = [&](int i) { return __ldg(&p.x[(n_first + (uint32_t)i) & nmask]); };
+        auto sink = [&](int i, float2 v, int) { xb[padi(i)] = v; };
+        group_fft<LOGB, -1>(work0, work1, p.tw, t, bar_id, src, sink, pre);
+    }
+    group_sync<T>(bar_id);
+    const int vlen = min(p.V, p.N - n0);
+    float psum[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) psum[s] = 0.f;
+    for (int m = 0; m < p.M; ++m) {
+        const float2* __restrict__ gm = p.gb + (size_t)m * B;
+        const bool in_sum = (m >= p.mask_lo && m < p.mask_hi);
+        auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
+        auto sink = [&](int i, float2 v, int slot) {
+            const int rel = i - p.Lpos;
+            const float mag = cabs2(v);
+            if (in_sum) psum[slot] += mag;
+            if (rel >= 0 && rel < vlen) {
+                const size_t o = (size_t)m * p.N + n0 + rel;
+                p.ymag[o] = mag;
+                if (p.ycplx) p.ycplx[o] = v;
+            }
+        };
+        group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
+    }
+    // p[n]: replay the last pass's index map (slot -> output index) without data
+    {
+        constexpr int R = S::RLAST, NB = 16 / R, NS = B / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + b * T;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int i = j + dft_q<R>(s) * NS;
+                const int rel = i - p.Lpos;
+                if (rel >= 0 && rel < vlen) p.p[n0 + rel] = psum[b * R + s];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large 1-D FFT as two tiled passes (N = N1 * N2, "four-step"): each CTA transforms C vectors
+// of length B = 2^LOGB that are strided in global memory, staged through a shared tile so both
+// the load and the store are coalesced.  Used for the chunk spectrum X (a4, dem_base:557), the
+// timing-recovery spectrum (a13, dem_base:721) and the full-length search/demod path.
+//   value loaded for (vector v, element e):  load(v * in_vs + e * in_es)
+//   value stored for (vector v, element e):  store(v * out_vs + e * out_es, val)
+//   optional twiddle after the transform:    val *= exp(DIR * 2 pi i * v * e / Ntw)
+// ---------------------------------------------------------------------------------------------
+struct TileGeom {
+    int nvec;
+    long long in_vs, in_es, out_vs, out_es;
+    int v_fast_in, v_fast_out;   // 1: consecutive vectors are adjacent in memory (coalesce over v)
+    int twiddle;                 // apply inter-pass twiddle
+    float inv_ntw;
+    uint32_t ntw_mask;
+};
+
+template <int LOGB, int DIR, int C, typename Load, typename Store>
+__global__ void __launch_bounds__(C * FftShape<LOGB>::T) fft_tile_kernel(TileGeom g, const float2* __restrict__ tw,
+                                                                          Load load, Store store) {
+    using S = FftShape<LOGB>;
+    constexpr int B = S::B, T = S::T, NT = C * T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);   // [C][WORK]
+    float2* bufB = bufA + (size_t)C * S::WORK;            // [C][WORK]
+    const int v0 = blockIdx.x * C;
+    const int tid = threadIdx.x;
+    // ---- coalesced tile load ----
+    for (int i = tid; i < C * B; i += NT) {
+        int v, e;
+        if (g.v_fast_in) { v = i % C; e = i / C; } else { e = i % B; v = i / B; }
+        float2 val = make_float2(0.f, 0.f);
+        if (v0 + v < g.nvec) val = load((long long)(v0 + v) * g.in_vs + (long long)e * g.in_es);
+        bufA[(size_t)v * S::WORK + padi(e)] = val;
+    }
+    __syncthreads();
+    // ---- one group per vector ----
+    {
+        const int v = tid / T, t = tid % T;
+        float2* a = bufA + (size_t)v * S::WORK;
+        float2* b = bufB + (size_t)v * S::WORK;
+        // pass 0 reads a -> b, pass 1 b -> a, pass 2 a -> ...: final sink goes to the buffer the last
+        // pass does not read (b for odd NPASS, a for even NPASS).
+        float2* outbuf = (S::NPASS & 1) ? b : a;
+        const uint32_t vg = (uint32_t)(v0 + v);
+        auto src = [&](int i) { return a[padi(i)]; };
+        auto sink = [&](int i, float2 val, int) {
+            if (g.twiddle) {
+                float2 w = unit_phasor_neg((vg * (uint32_t)i) & g.ntw_mask, g.inv_ntw);
+                if (DIR > 0) w = cconj(w);
+                val = cmul(val, w);
+            }
+            outbuf[padi(i)] = val;
+        };
+        group_fft<LOGB, DIR>(b, a, tw, t, 1 + (v % 15), src, sink);
+    }
+    __syncthreads();
+    // ---- coalesced tile store ----
+    float2* outb = (S::NPASS & 1) ? bufB : bufA;
+    for (int i = tid; i < C * B; i += NT) {
+        int v, e;
+        if (g.v_fast_out) { v = i % C; e = i / C; } else { e = i % B; v = i / B; }
+        if (v0 + v < g.nvec)
+            store((long long)(v0 + v) * g.out_vs + (long long)e * g.out_es, outb[(size_t)v * S::WORK + padi(e)]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a14 findCodeRateAndPhase (kern:236-320) + the host arithmetic of dem_base:733-750 (float64).
+// Single CTA; lowest index wins ties.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) timing_kernel(const float2* __restrict__ Pf, int offset, int len, int N,
+                                                     int spsym_min, DevResult* __restrict__ res) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int x = threadIdx.x; x < len; x += blockDim.x) {
+        const float v = cabs2(Pf[offset + x]);
+        if (v > bv) { bv = v; bi = offset + x; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi)) { bv = s_v[w]; bi = s_i[w]; }
+        if (bi == 0x7fffffff) bi = offset;
+        const float2 z = Pf[bi];
+        const float phase = atan2f(z.y, z.x);
+        res->timing[0] = (float)bi;
+        res->timing[1] = phase;
+        res->timing[2] = cabs2(z);
+        double sp = (double)N / (double)(float)bi;                     // dem_base:735
+        double off = -(double)phase / 3.141592653589793 * sp / 2.0;    // dem_base:745
+        if (off < 0) off += sp - 1.0;                                  // dem_base:746-747
+        res->sp_sym = sp;
+        res->code_offset = off;
+        double spc = sp < (double)spsym_min ? (double)spsym_min : sp;  // dem_base:994-995
+        res->n_sym = (int)((double)N / spc);                           // dem_base:999
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a15 findCentres (kern:78-146), CENTRES_ABS only (the reference never passes another op,
+// dem_base:796).  One thread per symbol; bit-exact index arithmetic incl. the FFMA contraction.
+// ---------------------------------------------------------------------------------------------
+__global__ void centres_kernel(const float* __restrict__ ymag, const DevResult* __restrict__ res, int N, int M, int W,
+                               int spsym_min, int max_sym, int* __restrict__ out_sym, int* __restrict__ out_idx,
+                               float* __restrict__ out_mag) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const double spd = res->sp_sym < (double)spsym_min ? (double)spsym_min : res->sp_sym;
+    const int n_sym = min(res->n_sym, max_sym);
+    if (x >= n_sym) return;
+    const float spSym = (float)spd;                 // np.float32(spSym), dem_base:997
+    const float offset = (float)res->code_offset;   // np.float32(codePhase)
+    const int left = W / 2;
+    const float tbase = __fmaf_rn((float)x, spSym, -(float)left);   // FFMA R, R, -3 in the reference SASS
+    int arrayIdx = (int)__fadd_rn(tbase, offset);
+    int maxArrayIdx = arrayIdx + W;
+    int offsetComp = (int)offset;
+    if (arrayIdx < 0) {
+        offsetComp -= arrayIdx;
+        arrayIdx = 0;
+    }
+    if (maxArrayIdx > N) maxArrayIdx = N;
+    maxArrayIdx -= arrayIdx;
+    int maxIdx = -1, maxCentreIdx = -1;
+    float maxVal = 0.f;
+    if (arrayIdx < N) {
+        for (int m = 0; m < M; ++m) {
+            const float* row = ymag + (size_t)m * N + arrayIdx;
+            for (int k = 0; k < maxArrayIdx; ++k) {
+                const float v = row[k];
+                if (v > maxVal) {
+                    maxVal = v;
+                    maxIdx = m;
+                    maxCentreIdx = k;
+                }
+            }
+        }
+        out_sym[x] = maxIdx;
+        out_idx[x] = (int)__fadd_rn(__fadd_rn(tbase, (float)maxCentreIdx), (float)offsetComp);
+        out_mag[x] = maxVal;
+    }
+}
+
+// fp32 FMA peak probe: 16 independent FMA chains per thread.
+__global__ void fma_peak_kernel(float* sink, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) sink[threadIdx.x & 4095] = s;
+}
+
+// Small helpers --------------------------------------------------------------------------------
+__global__ void real_to_complex_kernel(const float* __restrict__ in, float2* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2(in[i], 0.f);
+}
+
+}  // namespace pcs

@@ -1,0 +1,853 @@
+// C ABI of the demodulator hot path: handle management, planning and kernel orchestration.
+// Declarations and the reference interfaces they replace: include/pycusdr_b200.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pycusdr_b200.h"
+#include "kernels.cuh"
+
+using namespace pcs;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(PCS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// Functors for the tiled FFT passes ------------------------------------------------------------
+struct LoadC {
+    const float2* p;
+    __device__ __forceinline__ float2 operator()(long long i) const { return __ldg(&p[i]); }
+};
+struct LoadR {
+    const float* p;
+    __device__ __forceinline__ float2 operator()(long long i) const { return make_float2(__ldg(&p[i]), 0.f); }
+};
+struct StoreC {
+    float2* p;
+    __device__ __forceinline__ void operator()(long long i, float2 v) const { p[i] = v; }
+};
+
+struct pcs_handle {
+    pcs_config cfg;
+    cudaStream_t stream = nullptr;
+    int N = 0, logN = 0, D = 0, M = 0, sm_count = 0;
+    int max_sym = 0, spsym_min = 0, i_high = 0, i_low = 0;
+    // overlap-save plan
+    int path = 0, logB = 0, G = 1, nblk = 0, V = 0, Lpos = 0, Lneg = 0, search_ctas = 0, search_smem = 0;
+    // large-FFT plan
+    int logN1 = 0, logN2 = 0;
+    std::map<int, float2*> tw;     // forward twiddle tables by log2 size
+    // device memory
+    std::vector<void*> dev_allocs;
+    int64_t dev_bytes = 0;
+    float2 *d_x = nullptr, *d_X = nullptr, *d_masks = nullptr, *d_gb = nullptr, *d_scratch = nullptr;
+    float2 *d_Pf = nullptr, *d_ycplx = nullptr, *d_sigwin = nullptr, *d_noisewin = nullptr;
+    const float2* d_x_cur = nullptr;   // chunk source of the current upload (d_x or external)
+    int* d_shifts = nullptr;
+    float *d_psum = nullptr, *d_pmax = nullptr, *d_Efull = nullptr, *d_E = nullptr, *d_peakv = nullptr;
+    int *d_pidx = nullptr, *d_peako = nullptr;
+    float *d_ymag = nullptr, *d_p = nullptr, *d_mag = nullptr;
+    int *d_sym = nullptr, *d_centre = nullptr;
+    DevResult* d_res = nullptr;
+    // pinned host memory
+    float2 *h_x = nullptr, *h_sigwin = nullptr, *h_noisewin = nullptr;
+    DevResult* h_res = nullptr;
+    float *h_E = nullptr, *h_mag = nullptr;
+    int *h_sym = nullptr, *h_centre = nullptr;
+    bool uploaded = false, searched = false, demodulated = false;
+    bool own_stream = true;
+    int bin_lo = 0, bin_hi = 0;        // Doppler rows this handle searches (bin sharding); default all
+    int win_cap = PCS_WINDOW_MAX;      // largest computeSNR window this Doppler grid can produce
+    int64_t launches = 0;
+    // optional per-stage CUDA-event timing (pcs_set_profiling)
+    bool profiling = false;
+    cudaEvent_t ev[2 * PCS_NUM_STAGES] = {};
+    bool ev_pending[PCS_NUM_STAGES] = {};
+    double stage_ms[PCS_NUM_STAGES] = {};
+    int64_t stage_count[PCS_NUM_STAGES] = {};
+};
+
+// Stage timer: records a CUDA event pair on the handle's stream around a stage when profiling is on.
+struct StageTimer {
+    pcs_handle* h;
+    int stage;
+    StageTimer(pcs_handle* h_, int stage_) : h(h_), stage(stage_) {
+        if (!h->profiling) return;
+        if (h->ev_pending[stage]) {   // harvest the previous measurement of this stage
+            float ms = 0.f;
+            if (cudaEventSynchronize(h->ev[2 * stage + 1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, h->ev[2 * stage], h->ev[2 * stage + 1]) == cudaSuccess) {
+                h->stage_ms[stage] += ms;
+                h->stage_count[stage]++;
+            }
+            h->ev_pending[stage] = false;
+        }
+        cudaEventRecord(h->ev[2 * stage], h->stream);
+    }
+    ~StageTimer() {
+        if (!h->profiling) return;
+        cudaEventRecord(h->ev[2 * stage + 1], h->stream);
+        h->ev_pending[stage] = true;
+    }
+};
+
+template <typename T>
+static int dev_alloc(pcs_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc(&q, bytes));
+    h->dev_allocs.push_back(q);
+    h->dev_bytes += (int64_t)bytes;
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+static int get_twiddles(pcs_handle* h, int logB, const float2** out) {
+    auto it = h->tw.find(logB);
+    if (it == h->tw.end()) {
+        const int B = 1 << logB;
+        std::vector<float2> host(B);
+        for (int t = 0; t < B; ++t) {
+            const double a = -2.0 * M_PI * (double)t / (double)B;
+            host[t] = make_float2((float)cos(a), (float)sin(a));
+        }
+        float2* d = nullptr;
+        if (int rc = dev_alloc(h, &d, (size_t)B)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d, host.data(), sizeof(float2) * B, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        it = h->tw.emplace(logB, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// ---- tiled FFT pass launcher ------------------------------------------------------------------
+template <int LOGB, int DIR, int C, typename Load, typename Store>
+static int launch_tile_t(pcs_handle* h, const TileGeom& g, Load ld, Store st) {
+    using S = FftShape<LOGB>;
+    static_assert(S::T <= 32 || C <= 15, "named barrier ids");
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(h, LOGB, &tw)) return rc;
+    const size_t smem = (size_t)2 * C * S::WORK * sizeof(float2);
+    auto kern = fft_tile_kernel<LOGB, DIR, C, Load, Store>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = (g.nvec + C - 1) / C;
+    kern<<<grid, C * S::T, smem, h->stream>>>(g, tw, ld, st);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int DIR, typename Load, typename Store>
+static int launch_tile(pcs_handle* h, int logB, const TileGeom& g, Load ld, Store st) {
+    switch (logB) {
+        case 6: return launch_tile_t<6, DIR, 32>(h, g, ld, st);
+        case 7: return launch_tile_t<7, DIR, 32>(h, g, ld, st);
+        case 8: return launch_tile_t<8, DIR, 16>(h, g, ld, st);
+        case 9: return launch_tile_t<9, DIR, 16>(h, g, ld, st);
+        case 10: return launch_tile_t<10, DIR, 8>(h, g, ld, st);
+        case 11: return launch_tile_t<11, DIR, 4>(h, g, ld, st);
+        case 12: return launch_tile_t<12, DIR, 2>(h, g, ld, st);
+    }
+    return fail(PCS_ERR_INVALID, "unsupported tile transform size 2^%d", logB);
+}
+
+// N-point transform out = FFT_DIR(load(.)) through d_scratch (two passes).
+template <int DIR, typename Load>
+static int fft_large(pcs_handle* h, Load ld, float2* out) {
+    const int N1 = 1 << h->logN1, N2 = 1 << h->logN2;
+    TileGeom g1{};
+    g1.nvec = N2;
+    g1.in_vs = 1; g1.in_es = N2; g1.out_vs = 1; g1.out_es = N2;
+    g1.v_fast_in = 1; g1.v_fast_out = 1;
+    g1.twiddle = 1; g1.inv_ntw = 1.0f / (float)h->N; g1.ntw_mask = (uint32_t)h->N - 1u;
+    if (int rc = launch_tile<DIR>(h, h->logN1, g1, ld, StoreC{h->d_scratch})) return rc;
+    TileGeom g2{};
+    g2.nvec = N1;
+    g2.in_vs = N2; g2.in_es = 1; g2.out_vs = 1; g2.out_es = N1;
+    g2.v_fast_in = 0; g2.v_fast_out = 1;
+    g2.twiddle = 0; g2.inv_ntw = 0.f; g2.ntw_mask = 0;
+    return launch_tile<DIR>(h, h->logN2, g2, LoadC{h->d_scratch}, StoreC{out});
+}
+
+// ---- overlap-save launchers ---------------------------------------------------------------------
+template <int LOGB, int G>
+static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p) {
+    using S = FftShape<LOGB>;
+    constexpr int NW = (S::T + 31) / 32;
+    const size_t smem = (size_t)G * 3 * S::WORK * sizeof(float2) + (size_t)G * p.M * NW * 3 * sizeof(float);
+    auto kern = search_os_kernel<LOGB, G>;
+    static size_t configured = 0;
+    if (configured < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long long items = (long long)p.nblk * p.D;
+    const int grid = (int)((items + G - 1) / G);
+    h->search_ctas = grid;
+    h->search_smem = (int)smem;
+    kern<<<grid, G * S::T, smem, h->stream>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int LOGB, int G>
+static int launch_demod_os_t(pcs_handle* h, const OsDemodParams& p) {
+    using S = FftShape<LOGB>;
+    const size_t smem = (size_t)G * 3 * S::WORK * sizeof(float2);
+    auto kern = demod_os_kernel<LOGB, G>;
+    static size_t configured = 0;
+    if (configured < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = (p.nblk + G - 1) / G;
+    kern<<<grid, G * S::T, smem, h->stream>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int launch_search_os(pcs_handle* h, const OsSearchParams& p) {
+    switch (h->logB) {
+        case 9: return launch_search_os_t<9, 8>(h, p);
+        case 10: return launch_search_os_t<10, 4>(h, p);
+        case 11: return launch_search_os_t<11, 2>(h, p);
+        case 12: return launch_search_os_t<12, 1>(h, p);
+        case 13: return launch_search_os_t<13, 1>(h, p);
+    }
+    return fail(PCS_ERR_INVALID, "unsupported overlap-save block 2^%d", h->logB);
+}
+static int launch_demod_os(pcs_handle* h, const OsDemodParams& p) {
+    switch (h->logB) {
+        case 9: return launch_demod_os_t<9, 8>(h, p);
+        case 10: return launch_demod_os_t<10, 4>(h, p);
+        case 11: return launch_demod_os_t<11, 2>(h, p);
+        case 12: return launch_demod_os_t<12, 1>(h, p);
+        case 13: return launch_demod_os_t<13, 1>(h, p);
+    }
+    return fail(PCS_ERR_INVALID, "unsupported overlap-save block 2^%d", h->logB);
+}
+static int groups_for(int logB) { return logB == 9 ? 8 : logB == 10 ? 4 : logB == 11 ? 2 : 1; }
+
+// ---- planning ---------------------------------------------------------------------------------------
+// Time support of the filters: g_m = IFFT(Mk_m) has taps at n = 0..Lpos and n = -Lneg..-1 (circular).
+static int measure_support(pcs_handle* h, int* Lpos, int* Lneg) {
+    const int N = h->N, M = h->M;
+    std::vector<float2> g((size_t)N);
+    int lp = 0, ln = 0;
+    for (int m = 0; m < M; ++m) {
+        if (int rc = fft_large<+1>(h, LoadC{h->d_masks + (size_t)m * N}, h->d_X)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(g.data(), h->d_X, sizeof(float2) * N, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        double maxp = 0;
+        for (int n = 0; n < N; ++n) maxp = std::max(maxp, (double)g[n].x * g[n].x + (double)g[n].y * g[n].y);
+        const double thr = 1e-10 * maxp;   // 1e-5 in amplitude: far above complex64 rounding, far below any tap
+        for (int n = N / 2 - 1; n > lp; --n)
+            if ((double)g[n].x * g[n].x + (double)g[n].y * g[n].y > thr) { lp = n; break; }
+        for (int k = N / 2; k > ln; --k)
+            if ((double)g[N - k].x * g[N - k].x + (double)g[N - k].y * g[N - k].y > thr) { ln = k; break; }
+    }
+    *Lpos = lp;
+    *Lneg = ln;
+    return 0;
+}
+
+static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
+    const int N = h->N, M = h->M;
+    const int L = h->Lpos + h->Lneg + 1;
+    int best = 0;
+    double best_cost = 1e30;
+    const int lo = 9, hi = std::min(13, h->logN);
+    for (int lb = lo; lb <= hi; ++lb) {
+        const int B = 1 << lb, V = B - L + 1;
+        if (V < B / 2) continue;
+        const double cost = (double)lb * B / V;
+        if (cost < best_cost * 0.97) { best_cost = cost; best = lb; }   // prefer the smaller block on near ties
+    }
+    if (h->cfg.log2_block) {
+        best = h->cfg.log2_block;
+        if (best < lo || best > hi || (1 << best) - L + 1 < 1)
+            return fail(PCS_ERR_INVALID, "log2_block=%d cannot hold a filter support of %d taps", best, L);
+    }
+    if (!best) return PCS_ERR_INVALID;   // caller decides (AUTO falls back to FULL)
+    h->logB = best;
+    h->G = groups_for(best);
+    const int B = 1 << best;
+    h->V = B - L + 1;
+    h->nblk = (N + h->V - 1) / h->V;
+    // B-point filter spectra: Mk[m][k * N/B] * (N/B)
+    const int dec = N / B;
+    const float scale = (float)dec;
+    std::vector<float2> gb((size_t)M * B);
+    const float2* mk = reinterpret_cast<const float2*>(masks_host);
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k < B; ++k) {
+            const float2 v = mk[(size_t)m * N + (size_t)k * dec];
+            gb[(size_t)m * B + k] = make_float2(v.x * scale, v.y * scale);
+        }
+    if (int rc = dev_alloc(h, &h->d_gb, gb.size())) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->d_gb, gb.data(), sizeof(float2) * gb.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t np = (size_t)h->D * M * h->nblk;
+    if (int rc = dev_alloc(h, &h->d_psum, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_pmax, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_pidx, np)) return rc;
+    return 0;
+}
+
+// ---- public API -----------------------------------------------------------------------------------
+extern "C" {
+
+const char* pcs_last_error(void) { return g_last_error.c_str(); }
+int pcs_abi_version(void) { return PCS_ABI_VERSION; }
+
+int pcs_destroy(pcs_handle* h) {
+    if (!h) return PCS_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre};
+    for (void* p : pinned)
+        if (p) cudaFreeHost(p);
+    for (cudaEvent_t e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PCS_OK;
+}
+
+static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shifts, const float* masks) {
+    h->cfg = *cfg;
+    if (h->cfg.snr_window <= 0) h->cfg.snr_window = 5;
+    const int N = cfg->nfft;
+    if (N < (1 << 12) || N > (1 << 24) || (N & (N - 1)))
+        return fail(PCS_ERR_INVALID, "nfft must be a power of two in [2^12, 2^24], got %d", N);
+    if (cfg->num_masks < 1 || cfg->num_masks > 32)
+        return fail(PCS_ERR_INVALID, "num_masks must be in [1, 32], got %d", cfg->num_masks);
+    if (cfg->num_dopplers < 1 || cfg->element_offset < 0 || cfg->element_offset > 1)
+        return fail(PCS_ERR_INVALID, "bad Doppler grid (%d bins, offset %d)", cfg->num_dopplers, cfg->element_offset);
+    if (cfg->window_width < 1 || cfg->window_width > 63 || !(cfg->window_width & 1))
+        return fail(PCS_ERR_INVALID, "window_width must be odd and in [1, 63], got %d", cfg->window_width);
+    if (cfg->samples_per_sym < 2) return fail(PCS_ERR_INVALID, "samples_per_sym must be >= 2");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PCS_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PCS_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(PCS_ERR_NO_DEVICE, "device %s is sm_%d%d; this build targets sm_100a only", prop.name, prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->N = N;
+    h->logN = ilog2(N);
+    h->logN1 = h->logN / 2;
+    h->logN2 = h->logN - h->logN1;
+    h->D = cfg->num_dopplers + cfg->element_offset;
+    h->M = cfg->num_masks;
+    h->bin_lo = 0;
+    h->bin_hi = h->D;
+    const int D = h->D, M = h->M;
+    h->spsym_min = cfg->samples_per_sym / 2;                               // dem_base:104
+    if (h->spsym_min < 1) h->spsym_min = 1;
+    h->max_sym = N / h->spsym_min;                                         // dem_base:468
+    h->i_low = (int)((double)N / (0.9 * (double)cfg->samples_per_sym));    // dem_base:508-512
+    h->i_high = (int)((double)N / (1.1 * (double)cfg->samples_per_sym));
+    if (h->i_low > N / 2) h->i_low = N / 2;
+    for (int d = 0; d < D; ++d)
+        if (shifts[d] < 0 || shifts[d] >= N) return fail(PCS_ERR_INVALID, "shift[%d]=%d outside [0, nfft)", d, shifts[d]);
+    {   // largest window computeSNR can ask for: neighbouring bins' spacing + 2 * half width
+        int cap = 2 * h->cfg.snr_window;
+        for (int d = cfg->element_offset; d + 1 < D; ++d)
+            cap = std::max(cap, ((shifts[d + 1] - shifts[d]) & (N - 1)) + 2 * h->cfg.snr_window);
+        h->win_cap = std::min(cap, PCS_WINDOW_MAX);
+    }
+
+    if (int rc = dev_alloc(h, &h->d_x, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_X, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_scratch, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_Pf, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_masks, (size_t)M * N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_shifts, (size_t)D)) return rc;
+    if (int rc = dev_alloc(h, &h->d_Efull, (size_t)D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_E, (size_t)D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_peakv, (size_t)D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_peako, (size_t)D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_ymag, (size_t)M * N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_p, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_sym, (size_t)h->max_sym)) return rc;
+    if (int rc = dev_alloc(h, &h->d_centre, (size_t)h->max_sym)) return rc;
+    if (int rc = dev_alloc(h, &h->d_mag, (size_t)h->max_sym)) return rc;
+    if (int rc = dev_alloc(h, &h->d_sigwin, (size_t)PCS_WINDOW_MAX)) return rc;
+    if (int rc = dev_alloc(h, &h->d_noisewin, (size_t)PCS_WINDOW_MAX)) return rc;
+    if (int rc = dev_alloc(h, &h->d_res, (size_t)1)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_res, 0, sizeof(DevResult), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_sym, 0, sizeof(int) * h->max_sym, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_centre, 0, sizeof(int) * h->max_sym, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_mag, 0, sizeof(float) * h->max_sym, h->stream));
+
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_x, sizeof(float2) * N, cudaHostAllocDefault));
+    memset(h->h_x, 0, sizeof(float2) * N);
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_res, sizeof(DevResult), cudaHostAllocDefault));
+    memset(h->h_res, 0, sizeof(DevResult));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_E, sizeof(float) * D * M, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_sym, sizeof(int) * h->max_sym, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_centre, sizeof(int) * h->max_sym, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_mag, sizeof(float) * h->max_sym, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_sigwin, sizeof(float2) * PCS_WINDOW_MAX, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_noisewin, sizeof(float2) * PCS_WINDOW_MAX, cudaHostAllocDefault));
+
+    CUDA_TRY(cudaMemcpyAsync(h->d_masks, masks, sizeof(float2) * (size_t)M * N, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_shifts, shifts, sizeof(int) * D, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+
+    if (int rc = measure_support(h, &h->Lpos, &h->Lneg)) return rc;
+    const int want = cfg->path;
+    if (want == PCS_PATH_AUTO || want == PCS_PATH_OVERLAP_SAVE) {
+        int rc = plan_overlap_save(h, masks);
+        if (rc == 0) {
+            h->path = PCS_PATH_OVERLAP_SAVE;
+        } else if (want == PCS_PATH_OVERLAP_SAVE) {
+            return fail(PCS_ERR_INVALID, "filter time support (%d + %d taps) too long for the overlap-save path",
+                        h->Lpos, h->Lneg);
+        } else if (rc != PCS_ERR_INVALID) {
+            return rc;
+        }
+    }
+    if (h->path == 0)
+        return fail(PCS_ERR_INVALID, "path %d is not available in this build for a filter support of %d + %d taps",
+                    want, h->Lpos, h->Lneg);
+    return PCS_OK;
+}
+
+int pcs_create(const pcs_config* cfg, const int32_t* shifts, const float* masks, pcs_handle** out) {
+    if (!cfg || !shifts || !masks || !out) return fail(PCS_ERR_INVALID, "null argument");
+    if (cfg->abi_version != PCS_ABI_VERSION)
+        return fail(PCS_ERR_INVALID, "ABI version mismatch: caller %d, library %d", cfg->abi_version, PCS_ABI_VERSION);
+    pcs_handle* h = new pcs_handle();
+    int rc = create_impl(h, cfg, shifts, masks);
+    if (rc != PCS_OK) {
+        std::string keep = g_last_error;
+        pcs_destroy(h);
+        g_last_error = keep;
+        *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return PCS_OK;
+}
+
+void* pcs_host_buffer(pcs_handle* h) { return h ? (void*)h->h_x : nullptr; }
+int32_t pcs_max_symbols(const pcs_handle* h) { return h ? h->max_sym : 0; }
+int64_t pcs_launch_count(const pcs_handle* h) { return h ? h->launches : 0; }
+uint64_t pcs_stream(const pcs_handle* h) { return h ? (uint64_t)(uintptr_t)h->stream : 0; }
+
+int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
+    if (!h || !info) return fail(PCS_ERR_INVALID, "null argument");
+    info->path = h->path;
+    info->log2_block = h->logB;
+    info->valid_per_block = h->V;
+    info->num_blocks = h->nblk;
+    info->support_pos = h->Lpos;
+    info->support_neg = h->Lneg;
+    info->groups_per_cta = h->G;
+    info->search_ctas = (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
+    info->search_smem_bytes = h->search_smem;
+    info->sm_count = h->sm_count;
+    info->device_bytes = h->dev_bytes;
+    return PCS_OK;
+}
+
+// ---- enqueue helpers (no synchronisation) -------------------------------------------------------------
+static int enqueue_spectrum(pcs_handle* h) {
+    StageTimer t(h, PCS_STAGE_SPECTRUM);
+    return fft_large<-1>(h, LoadC{h->d_x_cur}, h->d_X);
+}
+
+static int enqueue_estimate(pcs_handle* h);
+
+// Search kernel + partial reduction for the handle's bin range [bin_lo, bin_hi).
+static int enqueue_search_local(pcs_handle* h) {
+    const int Dl = h->bin_hi - h->bin_lo;
+    const size_t row0 = (size_t)h->bin_lo * h->M;
+    OsSearchParams p{};
+    p.x = h->d_x_cur; p.gb = h->d_gb; p.shifts = h->d_shifts + h->bin_lo;
+    p.psum = h->d_psum + row0 * h->nblk; p.pmax = h->d_pmax + row0 * h->nblk; p.pidx = h->d_pidx + row0 * h->nblk;
+    p.N = h->N; p.D = Dl; p.M = h->M; p.nblk = h->nblk; p.V = h->V; p.Lpos = h->Lpos;
+    p.invN = 1.0f / (float)h->N;
+    const float2* twp = nullptr;
+    if (int rc = get_twiddles(h, h->logB, &twp)) return rc;
+    p.tw = twp;
+    {
+        StageTimer t(h, PCS_STAGE_SEARCH);
+        if (int rc = launch_search_os(h, p)) return rc;
+    }
+    StageTimer t2(h, PCS_STAGE_REDUCE);
+    const int DM = Dl * h->M;
+    search_reduce_kernel<<<(DM * 32 + 255) / 256, 256, 0, h->stream>>>(p.psum, p.pmax, p.pidx, DM, h->nblk,
+                                                                        h->d_Efull + row0, h->d_peakv + row0,
+                                                                        h->d_peako + row0);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_search(pcs_handle* h) {
+    if (int rc = enqueue_search_local(h)) return rc;
+    return enqueue_estimate(h);
+}
+
+// findDopplerEst + shift interpolation + peak + SNR windows over the full [D][M] energy table (which, with bin
+// sharding, the caller has all-gathered into d_Efull / d_peakv / d_peako beforehand).
+static int enqueue_estimate(pcs_handle* h) {
+    StageTimer t2(h, PCS_STAGE_ESTIMATE);
+    EstimateParams e{};
+    e.Efull = h->d_Efull; e.E = h->d_E; e.peak_val = h->d_peakv; e.peak_off = h->d_peako; e.shifts = h->d_shifts;
+    e.X = h->d_X; e.sig_win = h->d_sigwin; e.noise_win = h->d_noisewin; e.res = h->d_res;
+    e.D = h->D; e.M = h->M; e.N = h->N; e.num_dopplers = h->cfg.num_dopplers; e.element_offset = h->cfg.element_offset;
+    e.sum_all = h->cfg.sum_all_masks ? 1 : 0; e.window_width = h->cfg.snr_window;
+    estimate_kernel<<<1, 256, 0, h->stream>>>(e);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_demod(pcs_handle* h, int shift, bool want_complex) {
+    OsDemodParams p{};
+    p.x = h->d_x_cur; p.gb = h->d_gb; p.res = h->d_res; p.ymag = h->d_ymag; p.p = h->d_p;
+    p.ycplx = want_complex ? h->d_ycplx : nullptr;
+    p.N = h->N; p.M = h->M; p.nblk = h->nblk; p.V = h->V; p.Lpos = h->Lpos; p.shift_override = shift;
+    p.mask_lo = h->cfg.code_search_mask_offset; p.mask_hi = h->M - h->cfg.code_search_mask_offset;
+    p.invN = 1.0f / (float)h->N;
+    const float2* twp = nullptr;
+    if (int rc = get_twiddles(h, h->logB, &twp)) return rc;
+    p.tw = twp;
+    {
+        StageTimer t(h, PCS_STAGE_DEMOD_SURFACE);
+        if (int rc = launch_demod_os(h, p)) return rc;
+    }
+    if (want_complex) return 0;
+    StageTimer t2(h, PCS_STAGE_TIMING_SYMBOLS);
+    if (int rc = fft_large<-1>(h, LoadR{h->d_p}, h->d_Pf)) return rc;
+    timing_kernel<<<1, 1024, 0, h->stream>>>(h->d_Pf, h->i_high, h->i_low - h->i_high, h->N, h->spsym_min, h->d_res);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    centres_kernel<<<(h->max_sym + 255) / 256, 256, 0, h->stream>>>(h->d_ymag, h->d_res, h->N, h->M, h->cfg.window_width,
+                                                                  h->spsym_min, h->max_sym, h->d_sym, h->d_centre, h->d_mag);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_fetch_search(pcs_handle* h) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_E, h->d_E, sizeof(float) * h->D * h->M, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_sigwin, h->d_sigwin, sizeof(float2) * h->win_cap, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_noisewin, h->d_noisewin, sizeof(float2) * h->win_cap, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+static int enqueue_fetch_demod(pcs_handle* h) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_sym, h->d_sym, sizeof(int) * h->max_sym, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_centre, h->d_centre, sizeof(int) * h->max_sym, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_mag, h->d_mag, sizeof(float) * h->max_sym, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+static void copy_result(const pcs_handle* h, pcs_result* res) {
+    static_assert(sizeof(pcs_result) == sizeof(DevResult), "pcs_result and DevResult must have the same layout");
+    if (res) memcpy(res, h->h_res, sizeof(pcs_result));
+}
+static void copy_search_out(const pcs_handle* h, pcs_result* res, float* E_out) {
+    copy_result(h, res);
+    if (E_out) memcpy(E_out, h->h_E, sizeof(float) * h->D * h->M);
+}
+static void copy_demod_out(const pcs_handle* h, pcs_result* res, int32_t* sym, int32_t* centre, float* mag) {
+    copy_result(h, res);
+    const int n = std::min(std::max(h->h_res->n_sym, 0), h->max_sym);
+    if (sym) memcpy(sym, h->h_sym, sizeof(int) * n);
+    if (centre) memcpy(centre, h->h_centre, sizeof(int) * n);
+    if (mag) memcpy(mag, h->h_mag, sizeof(float) * n);
+}
+
+int pcs_upload(pcs_handle* h) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
+    h->d_x_cur = h->d_x;
+    h->uploaded = true;
+    h->searched = h->demodulated = false;
+    return enqueue_spectrum(h);
+}
+
+int pcs_upload_device(pcs_handle* h, const void* d_chunk) {
+    if (!h || !d_chunk) return fail(PCS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->d_x_cur = reinterpret_cast<const float2*>(d_chunk);
+    h->uploaded = true;
+    h->searched = h->demodulated = false;
+    return enqueue_spectrum(h);
+}
+
+int pcs_search(pcs_handle* h, pcs_result* res, float* E_out) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "pcs_search before pcs_upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = enqueue_search(h)) return rc;
+    if (int rc = enqueue_fetch_search(h)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->searched = true;
+    copy_search_out(h, res, E_out);
+    return PCS_OK;
+}
+
+int pcs_demod(pcs_handle* h, int32_t shift, pcs_result* res, int32_t* sym, int32_t* centre, float* mag) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "pcs_demod before pcs_upload");
+    if (shift < 0 && !h->searched) return fail(PCS_ERR_STATE, "pcs_demod(shift<0) needs a preceding pcs_search");
+    if (shift >= h->N) return fail(PCS_ERR_INVALID, "shift %d outside [0, nfft)", shift);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = enqueue_demod(h, shift, false)) return rc;
+    if (int rc = enqueue_fetch_demod(h)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->demodulated = true;
+    h->h_res->demod_shift = shift >= 0 ? shift : h->h_res->shift;
+    copy_demod_out(h, res, sym, centre, mag);
+    return PCS_OK;
+}
+
+int pcs_process(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "pcs_process before pcs_upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = enqueue_search(h)) return rc;
+    if (int rc = enqueue_demod(h, -1, false)) return rc;
+    if (int rc = enqueue_fetch_search(h)) return rc;
+    if (int rc = enqueue_fetch_demod(h)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->searched = h->demodulated = true;
+    h->h_res->demod_shift = h->h_res->shift;
+    copy_search_out(h, res, E_out);
+    copy_demod_out(h, res, sym, centre, mag);
+    return PCS_OK;
+}
+
+int pcs_enqueue_device(pcs_handle* h, const void* d_chunk) {
+    if (int rc = pcs_upload_device(h, d_chunk)) return rc;
+    if (int rc = enqueue_search(h)) return rc;
+    if (int rc = enqueue_demod(h, -1, false)) return rc;
+    h->searched = h->demodulated = true;
+    return PCS_OK;
+}
+
+int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->demodulated) return fail(PCS_ERR_STATE, "pcs_fetch before a chunk was enqueued");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = enqueue_fetch_search(h)) return rc;
+    if (int rc = enqueue_fetch_demod(h)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->h_res->demod_shift = h->h_res->shift;
+    copy_search_out(h, res, E_out);
+    copy_demod_out(h, res, sym, centre, mag);
+    return PCS_OK;
+}
+
+int pcs_snr_windows(pcs_handle* h, float* sig_win, float* noise_win) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->searched) return fail(PCS_ERR_STATE, "pcs_snr_windows before pcs_search");
+    if (sig_win) memcpy(sig_win, h->h_sigwin, sizeof(float2) * std::max(h->h_res->sig_len, 0));
+    if (noise_win) memcpy(noise_win, h->h_noisewin, sizeof(float2) * std::max(h->h_res->noise_len, 0));
+    return PCS_OK;
+}
+
+int pcs_get_spectrum(pcs_handle* h, float* X_out) {
+    if (!h || !X_out) return fail(PCS_ERR_INVALID, "null argument");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "no chunk uploaded");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(X_out, h->d_X, sizeof(float2) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PCS_OK;
+}
+
+int pcs_get_peaks(pcs_handle* h, float* peak_val, int32_t* peak_offset) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->searched) return fail(PCS_ERR_STATE, "pcs_get_peaks before pcs_search");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->D * h->M;
+    if (peak_val) CUDA_TRY(cudaMemcpyAsync(peak_val, h->d_peakv, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (peak_offset) CUDA_TRY(cudaMemcpyAsync(peak_offset, h->d_peako, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PCS_OK;
+}
+
+int pcs_get_demod_surface(pcs_handle* h, int32_t shift, float* y_out) {
+    if (!h || !y_out) return fail(PCS_ERR_INVALID, "null argument");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "no chunk uploaded");
+    if (shift < 0 || shift >= h->N) return fail(PCS_ERR_INVALID, "shift %d outside [0, nfft)", shift);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->d_ycplx)
+        if (int rc = dev_alloc(h, &h->d_ycplx, (size_t)h->M * h->N)) return rc;
+    if (int rc = enqueue_demod(h, shift, true)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_out, h->d_ycplx, sizeof(float2) * (size_t)h->M * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PCS_OK;
+}
+
+int pcs_get_demod_magnitudes(pcs_handle* h, float* ymag_out, float* p_out) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->demodulated) return fail(PCS_ERR_STATE, "no chunk demodulated");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (ymag_out)
+        CUDA_TRY(cudaMemcpyAsync(ymag_out, h->d_ymag, sizeof(float) * (size_t)h->M * h->N, cudaMemcpyDeviceToHost, h->stream));
+    if (p_out) CUDA_TRY(cudaMemcpyAsync(p_out, h->d_p, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PCS_OK;
+}
+
+int pcs_set_stream(pcs_handle* h, uint64_t stream) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) CUDA_TRY(cudaStreamDestroy(h->stream));
+    h->stream = reinterpret_cast<cudaStream_t>((uintptr_t)stream);
+    h->own_stream = false;
+    return PCS_OK;
+}
+
+int pcs_set_profiling(pcs_handle* h, int enable) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (enable && !h->ev[0])
+        for (cudaEvent_t& e : h->ev) CUDA_TRY(cudaEventCreate(&e));
+    if (!enable) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->profiling = enable != 0;
+    for (int s = 0; s < PCS_NUM_STAGES; ++s) {
+        h->ev_pending[s] = false;
+        h->stage_ms[s] = 0;
+        h->stage_count[s] = 0;
+    }
+    return PCS_OK;
+}
+
+int pcs_get_profile(pcs_handle* h, double* stage_ms, int64_t* stage_count) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (int s = 0; s < PCS_NUM_STAGES; ++s) {
+        if (h->ev_pending[s]) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventSynchronize(h->ev[2 * s + 1]));
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]));
+            h->stage_ms[s] += ms;
+            h->stage_count[s]++;
+            h->ev_pending[s] = false;
+        }
+        if (stage_ms) stage_ms[s] = h->stage_ms[s];
+        if (stage_count) stage_count[s] = h->stage_count[s];
+    }
+    return PCS_OK;
+}
+
+// fp32 FMA throughput of the device (roofline denominator for the FFT-bound kernels).
+int pcs_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(PCS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    float* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(float) * 4096));
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 1 << 14;
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(a));
+        fma_peak_kernel<<<grid, block>>>(sink, iters, 1.0001f, 0.9999f);
+        CUDA_TRY(cudaEventRecord(b));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 16 * (double)iters * grid * block;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops = best;
+    return PCS_OK;
+}
+
+// ---- bin sharding (one process per GPU; the exchange itself is an NCCL all-gather issued by the caller) ----
+int pcs_set_bin_range(pcs_handle* h, int32_t lo, int32_t hi) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (lo < 0 || hi > h->D || lo >= hi) return fail(PCS_ERR_INVALID, "bin range [%d, %d) outside [0, %d)", lo, hi, h->D);
+    h->bin_lo = lo;
+    h->bin_hi = hi;
+    return PCS_OK;
+}
+
+int pcs_shard_buffers(pcs_handle* h, void** d_energy, void** d_peak_val, void** d_peak_off) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (d_energy) *d_energy = h->d_Efull;
+    if (d_peak_val) *d_peak_val = h->d_peakv;
+    if (d_peak_off) *d_peak_off = h->d_peako;
+    return PCS_OK;
+}
+
+int pcs_enqueue_search_local(pcs_handle* h) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "search before upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return enqueue_search_local(h);
+}
+
+int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "estimate before upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = enqueue_estimate(h)) return rc;
+    h->searched = true;
+    if (with_demod) {
+        if (int rc = enqueue_demod(h, -1, false)) return rc;
+        h->demodulated = true;
+    }
+    return PCS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,13 @@
+"""UHF backend: forward FFT + Doppler search, then demodulation at the found bin
+(reference pyCuSDR/demodulator/UHF.py:5-20; input thresholding is disabled there, :14)."""
+from .demodulator_base import Demodulator as Demodulator_base
+
+
+class Demodulator(Demodulator_base):
+
+    def uploadAndFindCarrier(self, samples):
+        self.uploadToGPU(samples)
+        return self.findUHF(samples)
+
+    def demodulate(self):
+        return self.demodulateUHF()
