@@ -159,7 +159,10 @@ def test_stream_bits_match_oracle_per_chunk(mod, cfg, snr):
         if c == 0:
             # the filters' leading edge over the zero-filled overlap sees 1..L-1 samples only; constant-envelope
             # (FSK) filters tie exactly there, so those decisions are rounding noise as well
-            live &= lo["centres"] >= dem.sigOverlap + 2 * dem.spsym * conf["GPU"]["UHF"]["xcorrMaskSize"]
+            edge = 2 * dem.spsym * conf["GPU"]["UHF"]["xcorrMaskSize"]
+            live &= lo["centres"] >= dem.sigOverlap + edge
+            # ... and the circular correlation wraps the chunk's last L-1 outputs onto that same zero stretch
+            live &= lo["centres"] < dem.Nfft - edge
         assert len(ld["sym"]) == len(lo["sym"])
         np.testing.assert_array_equal(ld["sym"][live], lo["sym"][live], err_msg=f"chunk {c}: symbols")
         np.testing.assert_array_equal(ld["centres"][live], lo["centres"][live], err_msg=f"chunk {c}: centres")
