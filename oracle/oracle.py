@@ -52,6 +52,17 @@ def abs2(z):
     return (z.real * z.real + z.imag * z.imag).astype(F32, copy=False)
 
 
+def abs2_fma(z, order="xy"):
+    """abs2 as nvcc contracts the reference's ComplexAbsSquared (kern:1022-1026) on sm_100a: one FMUL and one
+    FFMA, i.e. fma(x, x, round(y*y)) ("xy") or fma(y, y, round(x*x)) ("yx").  Emulated through float64 (the
+    product of two float32 is exact there).  Which operand order the compiler picked is established by
+    tests/test_oracle_refgpu.py against the reference kernels' own output."""
+    z = np.asarray(z)
+    a, b = (z.real, z.imag) if order == "xy" else (z.imag, z.real)
+    bb = (b.astype(F32) * b.astype(F32)).astype(F32)
+    return (a.astype(np.float64) * a.astype(np.float64) + bb.astype(np.float64)).astype(F32)
+
+
 # --------------------------------------------------------------------------------------
 # a1: Doppler grid (dem_base:130-165)
 # --------------------------------------------------------------------------------------
@@ -290,7 +301,7 @@ def code_rate_band(Nfft, spsym):
     return int(Nfft / (1.1 * spsym)), int(Nfft / (0.9 * spsym))
 
 
-def find_code_rate_and_phase(Pf, offset, length):
+def find_code_rate_and_phase(Pf, offset, length, abs2=abs2):
     """[index of max, atan2 at max, max abs2] over Pf[offset:offset+length] (kern:236-320).
     Ties: lowest index (the reference is lane-order dependent on exact ties)."""
     band = abs2(Pf[offset:offset + length])
