@@ -380,7 +380,7 @@ def main():
     s_ms, s_cnt = prof["search"]
     search_ms = s_ms / max(s_cnt, 1)
     roof = {
-        "bound": "fp32", "kernel": "search_os_kernel",
+        "bound": "fp32", "kernel": "search_os256_kernel" if plan["log2_block"] == 8 else "search_os_kernel",
         "achieved": k_flop / (search_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": k_flop / (search_ms * 1e-3) / 1e12 / fp32_peak,
         "peak_source": "measured FMA loop on this GPU (pcs_measure_fp32_peak); nominal 74.4",

@@ -174,6 +174,222 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSear
 }
 
 // ---------------------------------------------------------------------------------------------
+// a6 + a7 + a8 fused, register-resident form for short filters (B = 256 = 16 x 16).
+// One group = 16 lanes (half a warp), 16 points per lane.  With a two-pass radix-16 autosort transform lane t
+// consumes inputs t + 16 r and produces outputs t + 16 q, so the block spectrum a forward transform leaves in a
+// lane's registers is exactly what pass 0 of the inverse transforms wants from that lane: the spectrum never
+// touches shared memory, every transform needs ONE 2 KB shared-memory exchange, the 15 inter-pass twiddles
+// W_256^(t r) are per-lane constants held in registers, and the filter spectra arrive as float4 (layout
+// [m][r/2][t][r%2]).  The epilogue keeps sum |y|^2 and max |y|^2 only; the offset of the maximum is recovered
+// by peak_locate256_kernel for the one winning block of each (bin, mask).
+// Partials are stored [block][bin][mask] so a group's M results are one contiguous store.
+// ---------------------------------------------------------------------------------------------
+struct Os256Params {
+    const float2* __restrict__ x;       // [N] chunk in HBM
+    const float4* __restrict__ gperm;   // [M][8][16] float4 = filter spectra (x N/256), lane-major pairs
+    const float2* __restrict__ tw;      // [256] exp(-2 pi i t / 256)
+    const int* __restrict__ shifts;     // [D]
+    float* __restrict__ psum;           // [nblk][D][M]
+    float* __restrict__ pmax;           // [nblk][D][M]
+    int N, D, M, nblk, V, Lpos;
+    float invN;
+};
+
+PCS_DEVINL float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// 256-point transform of one 16-lane group. In: v[r] = in[t + 16 r]. Out: slot s holds out[t + 16 dft_q<16>(s)].
+// tw[r] = exp(-2 pi i t r / 256).  buf: the group's 272-float2 exchange buffer.
+template <int DIR>
+PCS_DEVINL void fft256_regs(float2* v, float2* buf, const float2* tw, int t) {
+    Dft<16, DIR>::run(v);
+    __syncwarp();                      // previous transform's loads are done before the buffer is overwritten
+#pragma unroll
+    for (int s = 0; s < 16; ++s) buf[17 * t + dft_q<16>(s)] = v[s];      // natural index 16 t + q, padded
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[t + 17 * r];                 // natural index t + 16 r, padded
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = DIR < 0 ? cmul(v[r], tw[r]) : cmulc(v[r], tw[r]);
+    Dft<16, DIR>::run(v);
+}
+
+struct Os256Item {
+    int blk, d, n0, vlen;
+    uint32_t shift, n_first, nmask;
+};
+
+PCS_DEVINL Os256Item os256_item(const Os256Params& p, long long item) {
+    Os256Item it;
+    it.blk = (int)(item / p.D);
+    it.d = (int)(item % p.D);
+    it.nmask = (uint32_t)p.N - 1u;
+    it.shift = (uint32_t)p.shifts[it.d];
+    it.n0 = it.blk * p.V;
+    it.n_first = (uint32_t)(it.n0 - p.Lpos) & it.nmask;
+    it.vlen = min(p.V, p.N - it.n0);
+    return it;
+}
+
+// Block spectrum of the Doppler-rotated block (== spectrum shift by s_d, kern:370), natural order r -> X[t + 16 r].
+PCS_DEVINL void os256_block_spectrum(const Os256Params& p, const Os256Item& it, float2* buf, const float2* tw, int t,
+                                     float2* xb) {
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = __ldg(&p.x[(it.n_first + (uint32_t)(t + 16 * r)) & it.nmask]);
+    const uint32_t n = (it.n_first + (uint32_t)t) & it.nmask;
+    const float2 base = unit_phasor_neg((it.shift * n) & it.nmask, p.invN);
+    const float2 step = unit_phasor_neg((it.shift * 16u) & it.nmask, p.invN);
+    apply_twiddle_powers<16>(v, step);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = cmul(v[r], base);
+    fft256_regs<-1>(v, buf, tw, t);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) xb[r] = v[dft_q<16>(r)];     // dft_q<16> is an involution
+}
+
+// y = IFFT(xb * G_m) for one filter, left in slot order (slot s <-> output index t + 16 dft_q<16>(s)).
+PCS_DEVINL void os256_filter(const Os256Params& p, int m, const float2* xb, float2* buf, const float2* tw, int t,
+                             float2* v) {
+    const float4* __restrict__ g4 = p.gperm + (size_t)m * 128 + t;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const float4 g = __ldg(&g4[rr * 16]);
+        v[2 * rr] = cmul(xb[2 * rr], make_float2(g.x, g.y));
+        v[2 * rr + 1] = cmul(xb[2 * rr + 1], make_float2(g.z, g.w));
+    }
+    fft256_regs<+1>(v, buf, tw, t);
+}
+
+PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, int t) {
+    unsigned vm = 0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int rel = t + 16 * dft_q<16>(s) - p.Lpos;
+        if (rel >= 0 && rel < it.vlen) vm |= 1u << s;
+    }
+    return vm;
+}
+
+__global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
+    __shared__ float2 sbuf[16][272];
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    float2* buf = sbuf[g];
+    float2 tw[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
+    tw[0] = make_float2(1.f, 0.f);
+    const long long total = (long long)p.nblk * p.D;
+    long long item = (long long)blockIdx.x * 16 + g;
+    const bool live = item < total;
+    if (!live) item = total - 1;          // keep the warp convergent; results of the duplicate are dropped
+    const Os256Item it = os256_item(p, item);
+    float2 xb[16];
+    os256_block_spectrum(p, it, buf, tw, t, xb);
+    const unsigned vm = os256_valid_mask(p, it, t);
+    float ks0 = 0.f, ks1 = 0.f, kb0 = 0.f, kb1 = 0.f;
+    for (int m = 0; m < p.M; ++m) {
+        float2 v[16];
+        os256_filter(p, m, xb, buf, tw, t, v);
+        float sum = 0.f, best = 0.f;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const float mag = (vm >> s) & 1u ? cabs2(v[s]) : 0.f;
+            sum += mag;
+            best = fmaxf(best, mag);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (t == (m & 15)) {
+            if (m < 16) { ks0 = sum; kb0 = best; } else { ks1 = sum; kb1 = best; }
+        }
+    }
+    if (live) {
+        const size_t o = ((size_t)it.blk * p.D + it.d) * p.M;
+        if (t < p.M) { p.psum[o + t] = ks0; p.pmax[o + t] = kb0; }
+        if (t + 16 < p.M) { p.psum[o + t + 16] = ks1; p.pmax[o + t + 16] = kb1; }
+    }
+}
+
+// Column reduction of the [nblk][DM] partials in a fixed order: E, the peak value and the first block holding it.
+__global__ void __launch_bounds__(1024) search_reduce256_kernel(const float* __restrict__ psum,
+                                                                const float* __restrict__ pmax, int DM, int nblk,
+                                                                float* __restrict__ Efull, float* __restrict__ peak_val,
+                                                                int* __restrict__ win_blk) {
+    __shared__ float s_sum[32][33], s_max[32][33];
+    __shared__ int s_blk[32][33];
+    const int col = blockIdx.x * 32 + threadIdx.x, w = threadIdx.y;
+    float sum = 0.f, best = -1.f;
+    int bb = 0x7fffffff;
+    if (col < DM) {
+        for (int b = w; b < nblk; b += 32) {
+            const size_t o = (size_t)b * DM + col;
+            sum += psum[o];
+            const float v = pmax[o];
+            if (v > best) { best = v; bb = b; }
+        }
+    }
+    s_sum[w][threadIdx.x] = sum;
+    s_max[w][threadIdx.x] = best;
+    s_blk[w][threadIdx.x] = bb;
+    __syncthreads();
+    if (w == 0 && col < DM) {
+        for (int k = 1; k < 32; ++k) {
+            sum += s_sum[k][threadIdx.x];
+            const float v = s_max[k][threadIdx.x];
+            const int b = s_blk[k][threadIdx.x];
+            if (v > best || (v == best && b < bb)) { best = v; bb = b; }
+        }
+        Efull[col] = sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
+        peak_val[col] = best;
+        win_blk[col] = bb == 0x7fffffff ? 0 : bb;
+    }
+}
+
+// Offset of the maximum inside the winning block of every (bin, mask): lowest sample index wins ties.
+__global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, const int* __restrict__ win_blk,
+                                                                int* __restrict__ peak_off) {
+    __shared__ float2 sbuf[16][272];
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    float2* buf = sbuf[g];
+    float2 tw[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
+    tw[0] = make_float2(1.f, 0.f);
+    const int DM = p.D * p.M;
+    int col = blockIdx.x * 16 + g;
+    const bool live = col < DM;
+    if (!live) col = DM - 1;
+    const int d = col / p.M, m = col % p.M;
+    const Os256Item it = os256_item(p, (long long)win_blk[col] * p.D + d);
+    float2 xb[16], v[16];
+    os256_block_spectrum(p, it, buf, tw, t, xb);
+    os256_filter(p, m, xb, buf, tw, t, v);
+    float best = -1.f;
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int rel = t + 16 * dft_q<16>(s) - p.Lpos;
+        if (rel >= 0 && rel < it.vlen) {
+            const float mag = cabs2(v[s]);
+            const int n = it.n0 + rel;
+            if (mag > best || (mag == best && n < idx)) { best = mag; idx = n; }
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (live && t == 0) peak_off[col] = idx == 0x7fffffff ? 0 : idx;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Reduce the per-block partials (fixed order -> bit-reproducible, unlike the reference's float
 // atomics, kern:463,474).  One warp per (d, m).
 // ---------------------------------------------------------------------------------------------

@@ -79,6 +79,12 @@ struct pcs_handle {
     int *h_sym = nullptr, *h_centre = nullptr;
     bool uploaded = false, searched = false, demodulated = false;
     bool own_stream = true;
+    // register-resident B = 256 search plan (short filters)
+    bool fast256 = false;
+    int nblk256 = 0, V256 = 0;
+    float4* d_gperm = nullptr;
+    float *d_psum256 = nullptr, *d_pmax256 = nullptr;
+    int* d_winblk = nullptr;
     int bin_lo = 0, bin_hi = 0;        // Doppler rows this handle searches (bin sharding); default all
     int win_cap = PCS_WINDOW_MAX;      // largest computeSNR window this Doppler grid can produce
     int64_t launches = 0;
@@ -299,7 +305,7 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
         const double cost = (double)lb * B / V;
         if (cost < best_cost * 0.97) { best_cost = cost; best = lb; }   // prefer the smaller block on near ties
     }
-    if (h->cfg.log2_block) {
+    if (h->cfg.log2_block && h->cfg.log2_block != 8) {
         best = h->cfg.log2_block;
         if (best < lo || best > hi || (1 << best) - L + 1 < 1)
             return fail(PCS_ERR_INVALID, "log2_block=%d cannot hold a filter support of %d taps", best, L);
@@ -327,6 +333,36 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_psum, np)) return rc;
     if (int rc = dev_alloc(h, &h->d_pmax, np)) return rc;
     if (int rc = dev_alloc(h, &h->d_pidx, np)) return rc;
+    return 0;
+}
+
+// Search plan for filters short enough for 256-point blocks (at least half of every block is valid output).
+static int plan_fast256(pcs_handle* h, const float* masks_host) {
+    const int N = h->N, M = h->M, D = h->D;
+    const int L = h->Lpos + h->Lneg + 1;
+    const int V = 256 - L + 1;
+    if (V < 128 || N < 4096) return PCS_ERR_INVALID;
+    h->V256 = V;
+    h->nblk256 = (N + V - 1) / V;
+    const int dec = N / 256;
+    const float scale = (float)dec;
+    const float2* mk = reinterpret_cast<const float2*>(masks_host);
+    std::vector<float4> gp((size_t)M * 128);
+    for (int m = 0; m < M; ++m)
+        for (int rr = 0; rr < 8; ++rr)
+            for (int t = 0; t < 16; ++t) {
+                const float2 a = mk[(size_t)m * N + (size_t)(t + 16 * (2 * rr)) * dec];
+                const float2 b = mk[(size_t)m * N + (size_t)(t + 16 * (2 * rr + 1)) * dec];
+                gp[(size_t)m * 128 + rr * 16 + t] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+            }
+    if (int rc = dev_alloc(h, &h->d_gperm, gp.size())) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->d_gperm, gp.data(), sizeof(float4) * gp.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t np = (size_t)h->nblk256 * D * M;
+    if (int rc = dev_alloc(h, &h->d_psum256, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_pmax256, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_winblk, (size_t)D * M)) return rc;
+    h->fast256 = true;
     return 0;
 }
 
@@ -452,6 +488,12 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (h->path == 0)
         return fail(PCS_ERR_INVALID, "path %d is not available in this build for a filter support of %d + %d taps",
                     want, h->Lpos, h->Lneg);
+    if (cfg->log2_block == 0 || cfg->log2_block == 8) {
+        int rc = plan_fast256(h, masks);
+        if (rc != 0 && rc != PCS_ERR_INVALID) return rc;
+        if (rc != 0 && cfg->log2_block == 8)
+            return fail(PCS_ERR_INVALID, "log2_block=8 cannot hold a filter support of %d taps", h->Lpos + h->Lneg + 1);
+    }
     return PCS_OK;
 }
 
@@ -480,13 +522,14 @@ uint64_t pcs_stream(const pcs_handle* h) { return h ? (uint64_t)(uintptr_t)h->st
 int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
     if (!h || !info) return fail(PCS_ERR_INVALID, "null argument");
     info->path = h->path;
-    info->log2_block = h->logB;
-    info->valid_per_block = h->V;
-    info->num_blocks = h->nblk;
+    info->log2_block = h->fast256 ? 8 : h->logB;
+    info->valid_per_block = h->fast256 ? h->V256 : h->V;
+    info->num_blocks = h->fast256 ? h->nblk256 : h->nblk;
     info->support_pos = h->Lpos;
     info->support_neg = h->Lneg;
-    info->groups_per_cta = h->G;
-    info->search_ctas = (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
+    info->groups_per_cta = h->fast256 ? 16 : h->G;
+    info->search_ctas = h->fast256 ? (int)(((long long)h->nblk256 * h->D + 15) / 16)
+                                   : (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
     info->search_smem_bytes = h->search_smem;
     info->sm_count = h->sm_count;
     info->device_bytes = h->dev_bytes;
@@ -502,7 +545,39 @@ static int enqueue_spectrum(pcs_handle* h) {
 static int enqueue_estimate(pcs_handle* h);
 
 // Search kernel + partial reduction for the handle's bin range [bin_lo, bin_hi).
+static int enqueue_search_local256(pcs_handle* h) {
+    const int Dl = h->bin_hi - h->bin_lo, DM = Dl * h->M;
+    const size_t row0 = (size_t)h->bin_lo * h->M;
+    Os256Params p{};
+    p.x = h->d_x_cur; p.gperm = h->d_gperm; p.shifts = h->d_shifts + h->bin_lo;
+    p.psum = h->d_psum256; p.pmax = h->d_pmax256;
+    p.N = h->N; p.D = Dl; p.M = h->M; p.nblk = h->nblk256; p.V = h->V256; p.Lpos = h->Lpos;
+    p.invN = 1.0f / (float)h->N;
+    const float2* twp = nullptr;
+    if (int rc = get_twiddles(h, 8, &twp)) return rc;
+    p.tw = twp;
+    {
+        StageTimer t(h, PCS_STAGE_SEARCH);
+        const long long items = (long long)p.nblk * Dl;
+        h->search_ctas = (int)((items + 15) / 16);
+        h->search_smem = (int)(16 * 272 * sizeof(float2));
+        search_os256_kernel<<<h->search_ctas, 256, 0, h->stream>>>(p);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    StageTimer t2(h, PCS_STAGE_REDUCE);
+    search_reduce256_kernel<<<(DM + 31) / 32, dim3(32, 32), 0, h->stream>>>(p.psum, p.pmax, DM, p.nblk, h->d_Efull + row0,
+                                                                             h->d_peakv + row0, h->d_winblk + row0);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_winblk + row0, h->d_peako + row0);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_search_local(pcs_handle* h) {
+    if (h->fast256) return enqueue_search_local256(h);
     const int Dl = h->bin_hi - h->bin_lo;
     const size_t row0 = (size_t)h->bin_lo * h->M;
     OsSearchParams p{};

@@ -45,7 +45,8 @@ def test_chunk_spectrum_matches_fft(blockSize):
 
 
 @pytest.mark.parametrize("cfg,blockSize,log2_block", [
-    ("benchmark/bench_GMSK.json", 15, 0), ("benchmark/bench_GMSK.json", 15, 9), ("benchmark/bench_GMSK.json", 15, 11),
+    ("benchmark/bench_GMSK.json", 15, 0), ("benchmark/bench_GMSK.json", 15, 8), ("benchmark/bench_GMSK.json", 15, 9),
+    ("benchmark/bench_FSK.json", 12, 8), ("benchmark/bench_GMSK.json", 15, 11),
     ("benchmark/bench_GMSK.json", 15, 12), ("benchmark/bench_FSK.json", 14, 10), ("CC11xx.json", 16, 0),
     ("CC11xx.json", 16, 13), ("benchmark/bench_BPSK.json", 13, 0)])
 def test_search_energy_and_peaks_match_oracle(cfg, blockSize, log2_block):
