@@ -1,0 +1,70 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol include/pycusdr_b200.h
+declares, the ctypes binding covers the same list, and the product path fails loudly without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pycusdr_b200 import _native
+from tests.helpers import RADIO, have_gpu, load_conf, protocol_for
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pycusdr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_the_binding_binds():
+    assert _declared() == sorted(_native.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_native.LIB_PATH), "build with `make -C pycusdr_b200/csrc`"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} not exported"
+    assert _native.load().pcs_abi_version() == _native.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_native.Config) == 16 * 4
+    assert ctypes.sizeof(_native.Result) == 96
+    assert ctypes.sizeof(_native.PlanInfo) == 10 * 4 + 8
+
+
+def test_product_path_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pycusdr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+@pytest.mark.skipif(have_gpu(), reason="this checks the behaviour on a machine WITHOUT a GPU")
+def test_no_gpu_means_an_exception_not_a_fallback():
+    from pycusdr_b200.demodulator import UHF
+    conf = load_conf("benchmark/bench_GMSK.json")
+    with pytest.raises(_native.NativeError) as e:
+        UHF.Demodulator(conf, protocol_for(conf), RADIO)
+    assert e.value.code in (-3, -2)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_bad_arguments_are_rejected_before_touching_the_device():
+    lib = _native.load()
+    assert lib.pcs_create(None, None, None, None) == -1
+    assert b"null" in lib.pcs_last_error()
+    cfg = _native.Config(abi_version=99)
+    h = ctypes.c_void_p()
+    shifts = np.zeros(1, np.int32)
+    masks = np.zeros((1, 4096), np.complex64)
+    rc = lib.pcs_create(ctypes.byref(cfg), shifts.ctypes.data_as(ctypes.c_void_p), masks.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.byref(h))
+    assert rc == -1 and b"ABI version" in lib.pcs_last_error()
+    assert lib.pcs_destroy(None) == 0
