@@ -315,18 +315,20 @@ __global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
     }
 }
 
-// Column reduction of the [nblk][DM] partials in a fixed order: E, the peak value and the first block holding it.
+// Column reduction of the [nblk][DM] partials in a fixed order, stage 1: slice z of PCS_RED_SLICES takes blocks
+// z, z + S, z + 2S, ... and warp w of the CTA every 32nd of those; partial (sum, max, first block) per slice.
+#define PCS_RED_SLICES 8
 __global__ void __launch_bounds__(1024) search_reduce256_kernel(const float* __restrict__ psum,
                                                                 const float* __restrict__ pmax, int DM, int nblk,
-                                                                float* __restrict__ Efull, float* __restrict__ peak_val,
-                                                                int* __restrict__ win_blk) {
+                                                                float* __restrict__ part_sum, float* __restrict__ part_max,
+                                                                int* __restrict__ part_blk) {
     __shared__ float s_sum[32][33], s_max[32][33];
     __shared__ int s_blk[32][33];
-    const int col = blockIdx.x * 32 + threadIdx.x, w = threadIdx.y;
+    const int col = blockIdx.x * 32 + threadIdx.x, w = threadIdx.y, z = blockIdx.y;
     float sum = 0.f, best = -1.f;
     int bb = 0x7fffffff;
     if (col < DM) {
-        for (int b = w; b < nblk; b += 32) {
+        for (int b = z + PCS_RED_SLICES * w; b < nblk; b += PCS_RED_SLICES * 32) {
             const size_t o = (size_t)b * DM + col;
             sum += psum[o];
             const float v = pmax[o];
@@ -344,14 +346,19 @@ __global__ void __launch_bounds__(1024) search_reduce256_kernel(const float* __r
             const int b = s_blk[k][threadIdx.x];
             if (v > best || (v == best && b < bb)) { best = v; bb = b; }
         }
-        Efull[col] = sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
-        peak_val[col] = best;
-        win_blk[col] = bb == 0x7fffffff ? 0 : bb;
+        part_sum[(size_t)z * DM + col] = sum;
+        part_max[(size_t)z * DM + col] = best;
+        part_blk[(size_t)z * DM + col] = bb;
     }
 }
 
 // Offset of the maximum inside the winning block of every (bin, mask): lowest sample index wins ties.
-__global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, const int* __restrict__ win_blk,
+// Also stage 2 of the reduction: combines the PCS_RED_SLICES partials of its (bin, mask) in slice order and
+// writes E (kern:442 scale), the peak value and the winning block.
+__global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, const float* __restrict__ part_sum,
+                                                                const float* __restrict__ part_max,
+                                                                const int* __restrict__ part_blk,
+                                                                float* __restrict__ Efull, float* __restrict__ peak_val,
                                                                 int* __restrict__ peak_off) {
     __shared__ float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
@@ -365,7 +372,24 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
     const bool live = col < DM;
     if (!live) col = DM - 1;
     const int d = col / p.M, m = col % p.M;
-    const Os256Item it = os256_item(p, (long long)win_blk[col] * p.D + d);
+    int wblk;
+    {
+        float sum = part_sum[col], pk = part_max[col];
+        wblk = part_blk[col];
+#pragma unroll
+        for (int z = 1; z < PCS_RED_SLICES; ++z) {
+            sum += part_sum[(size_t)z * DM + col];
+            const float v = part_max[(size_t)z * DM + col];
+            const int b = part_blk[(size_t)z * DM + col];
+            if (v > pk || (v == pk && b < wblk)) { pk = v; wblk = b; }
+        }
+        if (wblk == 0x7fffffff) wblk = 0;
+        if (live && t == 0) {
+            Efull[col] = sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
+            peak_val[col] = pk;
+        }
+    }
+    const Os256Item it = os256_item(p, (long long)wblk * p.D + d);
     float2 xb[16], v[16];
     os256_block_spectrum(p, it, buf, tw, t, xb);
     os256_filter(p, m, xb, buf, tw, t, v);
@@ -425,11 +449,8 @@ struct EstimateParams {
     const float* __restrict__ peak_val; // [D][M]
     const int* __restrict__ peak_off;   // [D][M]
     const int* __restrict__ shifts;     // [D]
-    const float2* __restrict__ X;       // [N] chunk spectrum (may be null -> no windows)
-    float2* __restrict__ sig_win;       // [PCS_WINDOW_MAX]
-    float2* __restrict__ noise_win;     // [PCS_WINDOW_MAX]
     DevResult* __restrict__ res;
-    int D, M, N, num_dopplers, element_offset, sum_all, window_width;
+    int D, M, N, num_dopplers, element_offset, sum_all, window_width, window_cap;
 };
 
 __global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
@@ -437,30 +458,45 @@ __global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
     __shared__ float s_pk[256];
     __shared__ int s_pki[256];
     const int tid = threadIdx.x;
-    // 1. reference layout of E
-    for (int d = tid; d < p.D; d += blockDim.x) {
-        if (p.sum_all) {
-            float acc = p.Efull[(size_t)d * p.M];
-            for (int m = 1; m < p.M; ++m) acc += p.Efull[(size_t)d * p.M + m];   // kern:459-462
-            p.E[(size_t)d * p.M] = acc;
-            for (int m = 1; m < p.M; ++m) p.E[(size_t)d * p.M + m] = 0.f;
-        } else {
-            for (int m = 0; m < p.M; ++m) p.E[(size_t)d * p.M + m] = p.Efull[(size_t)d * p.M + m];
-        }
-    }
-    __syncthreads();
-    // 2. per-column running top-2 (kern:527-544), one thread per column
+    // 1 + 2. reference layout of E and the per-column running top-2 (kern:527-544, one thread per column), staged
+    // through shared memory 64 bins at a time so that the serial scan runs at shared-memory latency.
+    __shared__ float tile[64][33];
     const int ncols = p.sum_all ? 1 : p.M;
-    if (tid < ncols) {
-        float v0 = 0.f, v1 = 0.f;
-        int i0 = 0, i1 = 0, cur = 0;
-        for (int i = p.element_offset; i < p.num_dopplers + p.element_offset; ++i) {
-            const float e = p.E[(size_t)i * p.M + tid];
-            if (e > (cur ? v1 : v0)) {
-                if (cur) { v1 = e; i1 = i; } else { v0 = e; i0 = i; }
-                cur = (v0 >= v1) ? 1 : 0;
+    float v0 = 0.f, v1 = 0.f;
+    int i0 = 0, i1 = 0, cur = 0;
+    for (int base = 0; base < p.D; base += 64) {
+        const int rows = min(64, p.D - base);
+        if (p.sum_all) {
+            if (tid < rows) {
+                const float* src = p.Efull + (size_t)(base + tid) * p.M;
+                float acc = src[0];
+                for (int m = 1; m < p.M; ++m) acc += src[m];                          // kern:459-462
+                float* dst = p.E + (size_t)(base + tid) * p.M;
+                dst[0] = acc;
+                for (int m = 1; m < p.M; ++m) dst[m] = 0.f;
+                tile[tid][0] = acc;
+            }
+        } else {
+            for (int i = tid; i < rows * p.M; i += blockDim.x) {
+                const float e = p.Efull[(size_t)base * p.M + i];
+                p.E[(size_t)base * p.M + i] = e;
+                tile[i / p.M][i % p.M] = e;
             }
         }
+        __syncthreads();
+        if (tid < ncols) {
+            const int lo = max(base, p.element_offset), hi = min(base + rows, p.num_dopplers + p.element_offset);
+            for (int i = lo; i < hi; ++i) {
+                const float e = tile[i - base][tid];
+                if (e > (cur ? v1 : v0)) {
+                    if (cur) { v1 = e; i1 = i; } else { v0 = e; i0 = i; }
+                    cur = (v0 >= v1) ? 1 : 0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < ncols) {
         const float tmp = __fmaf_rn((float)i0, v0, __fmul_rn((float)i1, v1));   // SASS: FMUL + FFMA
         float bl = __fdiv_rn(tmp, __fadd_rn(v0, v1));
         float vl = __fdiv_rn(tmp, (float)(i0 + i1));
@@ -535,30 +571,23 @@ __global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
         }
     }
     __syncthreads();
-    // 4. spectrum windows for computeSNR: circular [s_lo - w, s_hi + w) and the same + N/2
-    if (p.X != nullptr) {
-        const DevResult* r = p.res;
-        int sig_start = 0, len = 0;
+    // 4. geometry of the spectrum windows computeSNR averages: circular [s_lo - w, s_hi + w) and the same + N/2
+    //    (the bins themselves are produced by spectrum_bins_kernel)
+    if (tid == 0) {
+        DevResult* r = p.res;
+        int sig_start = 0, len = 0, noise_start = 0;
         if (r->status == 0) {
             const int slo = p.shifts[r->low_idx], shi = p.shifts[r->high_idx];
             const int nmask = p.N - 1;
             sig_start = (slo - p.window_width) & nmask;
             len = ((shi - slo) & nmask) + 2 * p.window_width;
-            if (len > PCS_WINDOW_MAX) len = 0;      // host falls back to a full spectrum read
-            const int noise_start = (sig_start + p.N / 2) & nmask;
-            for (int i = tid; i < len; i += blockDim.x) {
-                p.sig_win[i] = p.X[(sig_start + i) & nmask];
-                p.noise_win[i] = p.X[(noise_start + i) & nmask];
-            }
-            if (tid == 0) {
-                p.res->sig_start = sig_start;
-                p.res->sig_len = len;
-                p.res->noise_start = noise_start;
-                p.res->noise_len = len;
-            }
-        } else if (tid == 0) {
-            p.res->sig_start = p.res->sig_len = p.res->noise_start = p.res->noise_len = 0;
+            if (len > p.window_cap) len = 0;      // host falls back to a full spectrum read
+            noise_start = (sig_start + p.N / 2) & nmask;
         }
+        r->sig_start = sig_start;
+        r->sig_len = len;
+        r->noise_start = noise_start;
+        r->noise_len = len;
     }
 }
 
@@ -642,6 +671,132 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) demod_os_kernel(OsDemod
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12 + a13 (first half), register-resident 256-point form: one group per block, all masks.
+// ---------------------------------------------------------------------------------------------
+struct Demod256Params {
+    Os256Params os;                      // x, gperm, tw, N, M, nblk, V, Lpos, invN (D / shifts / psum / pmax unused)
+    const DevResult* __restrict__ res;   // shift source when shift_override < 0
+    float* __restrict__ ymag;            // [M][N]
+    float* __restrict__ p;               // [N]
+    float2* __restrict__ ycplx;          // [M][N] or null
+    int shift_override, mask_lo, mask_hi;
+};
+
+__global__ void __launch_bounds__(64) demod_os256_kernel(Demod256Params q) {
+    __shared__ float2 sbuf[4][272];
+    const Os256Params& p = q.os;
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    float2* buf = sbuf[g];
+    float2 tw[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
+    tw[0] = make_float2(1.f, 0.f);
+    int blk = blockIdx.x * 4 + g;
+    const bool live = blk < p.nblk;
+    if (!live) blk = p.nblk - 1;
+    Os256Item it;
+    it.blk = blk;
+    it.d = 0;
+    it.nmask = (uint32_t)p.N - 1u;
+    it.shift = (uint32_t)(q.shift_override >= 0 ? q.shift_override : q.res->shift) & it.nmask;
+    it.n0 = blk * p.V;
+    it.n_first = (uint32_t)(it.n0 - p.Lpos) & it.nmask;
+    it.vlen = min(p.V, p.N - it.n0);
+    float2 xb[16];
+    os256_block_spectrum(p, it, buf, tw, t, xb);
+    float psum[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) psum[s] = 0.f;
+    for (int m = 0; m < p.M; ++m) {
+        float2 v[16];
+        os256_filter(p, m, xb, buf, tw, t, v);
+        const bool in_sum = (m >= q.mask_lo && m < q.mask_hi);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const float mag = cabs2(v[s]);
+            if (in_sum) psum[s] += mag;                       // mask order, like kern:197-201
+            const int rel = t + 16 * dft_q<16>(s) - p.Lpos;
+            if (live && rel >= 0 && rel < it.vlen) {
+                const size_t o = (size_t)m * p.N + it.n0 + rel;
+                q.ymag[o] = mag;
+                if (q.ycplx) q.ycplx[o] = v[s];
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int rel = t + 16 * dft_q<16>(s) - p.Lpos;
+        if (live && rel >= 0 && rel < it.vlen) q.p[it.n0 + rel] = psum[s];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pruned second pass of the four-step transform.  After pass 1 the scratch holds S[k1][n2] (twiddled); output bin
+// k = k1 + N1 k2 is sum_n2 S[k1][n2] W_N2^(n2 k2).  Timing recovery only looks at the symbol-rate band
+// [iH, iL) (dem_base:508-512), i.e. nk2 <= 16 consecutive k2 for every k1: one warp per k1 row, direct sums.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) band_dft_kernel(const float2* __restrict__ S, const float2* __restrict__ tw2,
+                                                       int N1, int N2, int k2lo, int nk2, float2* __restrict__ out) {
+    const int k1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k1 >= N1) return;
+    float2 acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+    const float2* row = S + (size_t)k1 * N2;
+    for (int n2 = lane; n2 < N2; n2 += 32) {
+        const float2 v = row[n2];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < nk2) {
+                const float2 w = __ldg(&tw2[(n2 * (k2lo + j)) & (N2 - 1)]);
+                acc[j].x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc[j].x));
+                acc[j].y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc[j].y));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < nk2) {
+            float2 a = acc[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+                a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+            }
+            if (lane == 0) out[(size_t)k1 + (size_t)N1 * (k2lo + j)] = a;
+        }
+    }
+}
+
+// Same idea for computeSNR (dem_base:635-667): the two circular spectrum windows the estimate selected, one warp
+// per bin.  Window geometry comes from the DevResult the estimate kernel just wrote.
+__global__ void __launch_bounds__(256) spectrum_bins_kernel(const float2* __restrict__ S, const float2* __restrict__ tw2,
+                                                            int N1, int N2, const DevResult* __restrict__ res,
+                                                            float2* __restrict__ sig_win, float2* __restrict__ noise_win) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int len = res->sig_len;
+    if (w >= 2 * len) return;
+    const int which = w >= len, i = which ? w - len : w;
+    const int N = N1 * N2;
+    const int k = ((which ? res->noise_start : res->sig_start) + i) & (N - 1);
+    const int k1 = k & (N1 - 1), k2 = k / N1;
+    const float2* row = S + (size_t)k1 * N2;
+    float2 a = make_float2(0.f, 0.f);
+    for (int n2 = lane; n2 < N2; n2 += 32) {
+        const float2 v = row[n2];
+        const float2 wv = __ldg(&tw2[(n2 * k2) & (N2 - 1)]);
+        a.x = fmaf(v.x, wv.x, fmaf(-v.y, wv.y, a.x));
+        a.y = fmaf(v.x, wv.y, fmaf(v.y, wv.x, a.y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+    }
+    if (lane == 0) (which ? noise_win : sig_win)[i] = a;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -83,8 +83,15 @@ struct pcs_handle {
     bool fast256 = false;
     int nblk256 = 0, V256 = 0;
     float4* d_gperm = nullptr;
-    float *d_psum256 = nullptr, *d_pmax256 = nullptr;
-    int* d_winblk = nullptr;
+    float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
+    int* d_part_blk = nullptr;
+    float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
+    bool spectrum_full = false;        // d_X holds the full spectrum of the current chunk (computed on demand)
+    // CUDA graph of the per-chunk sequence search -> estimate -> demod -> result copies (captured after one eager run)
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_enabled = true, graph_failed = false, fetch_in_flight = false;
+    int eager_chunks = 0;
+    int64_t graph_launches = 0;
     int bin_lo = 0, bin_hi = 0;        // Doppler rows this handle searches (bin sharding); default all
     int win_cap = PCS_WINDOW_MAX;      // largest computeSNR window this Doppler grid can produce
     int64_t launches = 0;
@@ -191,22 +198,49 @@ static int launch_tile(pcs_handle* h, int logB, const TileGeom& g, Load ld, Stor
     return fail(PCS_ERR_INVALID, "unsupported tile transform size 2^%d", logB);
 }
 
-// N-point transform out = FFT_DIR(load(.)) through d_scratch (two passes).
+// Same transform sizes with 4 vectors per CTA: four times the CTAs when a pass has too few vectors to fill the GPU.
+template <int DIR, typename Load, typename Store>
+static int launch_tile_narrow(pcs_handle* h, int logB, const TileGeom& g, Load ld, Store st) {
+    switch (logB) {
+        case 6: return launch_tile_t<6, DIR, 4>(h, g, ld, st);
+        case 7: return launch_tile_t<7, DIR, 4>(h, g, ld, st);
+        case 8: return launch_tile_t<8, DIR, 4>(h, g, ld, st);
+        case 9: return launch_tile_t<9, DIR, 4>(h, g, ld, st);
+    }
+    return launch_tile<DIR>(h, logB, g, ld, st);
+}
+
+// First pass of the four-step N-point transform: S[k1][n2] = W_N^(n2 k1) * sum_n1 in[n1 N2 + n2] W_N1^(n1 k1).
 template <int DIR, typename Load>
-static int fft_large(pcs_handle* h, Load ld, float2* out) {
-    const int N1 = 1 << h->logN1, N2 = 1 << h->logN2;
+static int fft_pass1(pcs_handle* h, Load ld, float2* S) {
+    const int N2 = 1 << h->logN2;
     TileGeom g1{};
     g1.nvec = N2;
     g1.in_vs = 1; g1.in_es = N2; g1.out_vs = 1; g1.out_es = N2;
     g1.v_fast_in = 1; g1.v_fast_out = 1;
     g1.twiddle = 1; g1.inv_ntw = 1.0f / (float)h->N; g1.ntw_mask = (uint32_t)h->N - 1u;
-    if (int rc = launch_tile<DIR>(h, h->logN1, g1, ld, StoreC{h->d_scratch})) return rc;
+    if (N2 / 16 < h->sm_count / 2) return launch_tile_narrow<DIR>(h, h->logN1, g1, ld, StoreC{S});
+    return launch_tile<DIR>(h, h->logN1, g1, ld, StoreC{S});
+}
+
+// Second pass: out[k1 + N1 k2] = sum_n2 S[k1][n2] W_N2^(n2 k2).
+template <int DIR>
+static int fft_pass2(pcs_handle* h, const float2* S, float2* out) {
+    const int N1 = 1 << h->logN1, N2 = 1 << h->logN2;
     TileGeom g2{};
     g2.nvec = N1;
     g2.in_vs = N2; g2.in_es = 1; g2.out_vs = 1; g2.out_es = N1;
     g2.v_fast_in = 0; g2.v_fast_out = 1;
     g2.twiddle = 0; g2.inv_ntw = 0.f; g2.ntw_mask = 0;
-    return launch_tile<DIR>(h, h->logN2, g2, LoadC{h->d_scratch}, StoreC{out});
+    if (N1 / 16 < h->sm_count / 2) return launch_tile_narrow<DIR>(h, h->logN2, g2, LoadC{S}, StoreC{out});
+    return launch_tile<DIR>(h, h->logN2, g2, LoadC{S}, StoreC{out});
+}
+
+// N-point transform out = FFT_DIR(load(.)) through d_scratch (two passes).
+template <int DIR, typename Load>
+static int fft_large(pcs_handle* h, Load ld, float2* out) {
+    if (int rc = fft_pass1<DIR>(h, ld, h->d_scratch)) return rc;
+    return fft_pass2<DIR>(h, h->d_scratch, out);
 }
 
 // ---- overlap-save launchers ---------------------------------------------------------------------
@@ -361,7 +395,9 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
     const size_t np = (size_t)h->nblk256 * D * M;
     if (int rc = dev_alloc(h, &h->d_psum256, np)) return rc;
     if (int rc = dev_alloc(h, &h->d_pmax256, np)) return rc;
-    if (int rc = dev_alloc(h, &h->d_winblk, (size_t)D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_sum, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_max, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_blk, (size_t)PCS_RED_SLICES * D * M)) return rc;
     h->fast256 = true;
     return 0;
 }
@@ -380,6 +416,7 @@ int pcs_destroy(pcs_handle* h) {
     void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -390,6 +427,7 @@ int pcs_destroy(pcs_handle* h) {
 static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shifts, const float* masks) {
     h->cfg = *cfg;
     if (h->cfg.snr_window <= 0) h->cfg.snr_window = 5;
+    h->graph_enabled = !(cfg->reserved[0] & 1);
     const int N = cfg->nfft;
     if (N < (1 << 12) || N > (1 << 24) || (N & (N - 1)))
         return fail(PCS_ERR_INVALID, "nfft must be a power of two in [2^12, 2^24], got %d", N);
@@ -437,6 +475,7 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (int rc = dev_alloc(h, &h->d_x, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_X, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_scratch, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_scratch2, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_Pf, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_masks, (size_t)M * N)) return rc;
     if (int rc = dev_alloc(h, &h->d_shifts, (size_t)D)) return rc;
@@ -537,9 +576,13 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
 }
 
 // ---- enqueue helpers (no synchronisation) -------------------------------------------------------------
+// a4 (dem_base:557).  Only the spectrum bins computeSNR averages are ever consumed per chunk (the search works on the
+// time-domain chunk), so the hot path runs pass 1 of the four-step transform here and spectrum_bins_kernel finishes
+// just those bins after the estimate; pcs_get_spectrum completes the full transform on demand.
 static int enqueue_spectrum(pcs_handle* h) {
     StageTimer t(h, PCS_STAGE_SPECTRUM);
-    return fft_large<-1>(h, LoadC{h->d_x_cur}, h->d_X);
+    h->spectrum_full = false;
+    return fft_pass1<-1>(h, LoadC{h->d_x_cur}, h->d_scratch);
 }
 
 static int enqueue_estimate(pcs_handle* h);
@@ -566,11 +609,12 @@ static int enqueue_search_local256(pcs_handle* h) {
         CUDA_TRY(cudaGetLastError());
     }
     StageTimer t2(h, PCS_STAGE_REDUCE);
-    search_reduce256_kernel<<<(DM + 31) / 32, dim3(32, 32), 0, h->stream>>>(p.psum, p.pmax, DM, p.nblk, h->d_Efull + row0,
-                                                                             h->d_peakv + row0, h->d_winblk + row0);
+    search_reduce256_kernel<<<dim3((DM + 31) / 32, PCS_RED_SLICES), dim3(32, 32), 0, h->stream>>>(
+        p.psum, p.pmax, DM, p.nblk, h->d_part_sum, h->d_part_max, h->d_part_blk);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_winblk + row0, h->d_peako + row0);
+    peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_part_sum, h->d_part_max, h->d_part_blk,
+                                                                  h->d_Efull + row0, h->d_peakv + row0, h->d_peako + row0);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -613,10 +657,46 @@ static int enqueue_estimate(pcs_handle* h) {
     StageTimer t2(h, PCS_STAGE_ESTIMATE);
     EstimateParams e{};
     e.Efull = h->d_Efull; e.E = h->d_E; e.peak_val = h->d_peakv; e.peak_off = h->d_peako; e.shifts = h->d_shifts;
-    e.X = h->d_X; e.sig_win = h->d_sigwin; e.noise_win = h->d_noisewin; e.res = h->d_res;
+    e.res = h->d_res;
     e.D = h->D; e.M = h->M; e.N = h->N; e.num_dopplers = h->cfg.num_dopplers; e.element_offset = h->cfg.element_offset;
-    e.sum_all = h->cfg.sum_all_masks ? 1 : 0; e.window_width = h->cfg.snr_window;
+    e.sum_all = h->cfg.sum_all_masks ? 1 : 0; e.window_width = h->cfg.snr_window; e.window_cap = h->win_cap;
     estimate_kernel<<<1, 256, 0, h->stream>>>(e);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    const float2* tw2 = nullptr;
+    if (int rc = get_twiddles(h, h->logN2, &tw2)) return rc;
+    spectrum_bins_kernel<<<(2 * h->win_cap + 7) / 8, 256, 0, h->stream>>>(h->d_scratch, tw2, 1 << h->logN1, 1 << h->logN2,
+                                                                          h->d_res, h->d_sigwin, h->d_noisewin);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_timing_spectrum(pcs_handle* h) {
+    // Pf = RFFT_N(p) (dem_base:721) restricted to the symbol-rate band findCodeRateAndPhase scans (dem_base:508-512)
+    const int N1 = 1 << h->logN1, N2 = 1 << h->logN2;
+    const int k2lo = h->i_high / N1, k2hi = std::max(h->i_low - 1, h->i_high) / N1, nk2 = k2hi - k2lo + 1;
+    if (int rc = fft_pass1<-1>(h, LoadR{h->d_p}, h->d_scratch2)) return rc;
+    if (nk2 > 16) return fft_pass2<-1>(h, h->d_scratch2, h->d_Pf);
+    const float2* tw2 = nullptr;
+    if (int rc = get_twiddles(h, h->logN2, &tw2)) return rc;
+    band_dft_kernel<<<(N1 + 7) / 8, 256, 0, h->stream>>>(h->d_scratch2, tw2, N1, N2, k2lo, nk2, h->d_Pf);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_demod_surface256(pcs_handle* h, int shift, bool want_complex) {
+    Demod256Params q{};
+    q.os.x = h->d_x_cur; q.os.gperm = h->d_gperm; q.os.N = h->N; q.os.M = h->M; q.os.nblk = h->nblk256; q.os.V = h->V256;
+    q.os.Lpos = h->Lpos; q.os.D = 1; q.os.invN = 1.0f / (float)h->N;
+    const float2* twp = nullptr;
+    if (int rc = get_twiddles(h, 8, &twp)) return rc;
+    q.os.tw = twp;
+    q.res = h->d_res; q.ymag = h->d_ymag; q.p = h->d_p; q.ycplx = want_complex ? h->d_ycplx : nullptr;
+    q.shift_override = shift;
+    q.mask_lo = h->cfg.code_search_mask_offset; q.mask_hi = h->M - h->cfg.code_search_mask_offset;
+    demod_os256_kernel<<<(h->nblk256 + 3) / 4, 64, 0, h->stream>>>(q);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -634,11 +714,15 @@ static int enqueue_demod(pcs_handle* h, int shift, bool want_complex) {
     p.tw = twp;
     {
         StageTimer t(h, PCS_STAGE_DEMOD_SURFACE);
-        if (int rc = launch_demod_os(h, p)) return rc;
+        if (h->fast256) {
+            if (int rc = enqueue_demod_surface256(h, shift, want_complex)) return rc;
+        } else {
+            if (int rc = launch_demod_os(h, p)) return rc;
+        }
     }
     if (want_complex) return 0;
     StageTimer t2(h, PCS_STAGE_TIMING_SYMBOLS);
-    if (int rc = fft_large<-1>(h, LoadR{h->d_p}, h->d_Pf)) return rc;
+    if (int rc = enqueue_timing_spectrum(h)) return rc;
     timing_kernel<<<1, 1024, 0, h->stream>>>(h->d_Pf, h->i_high, h->i_low - h->i_high, h->N, h->spsym_min, h->d_res);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -678,6 +762,53 @@ static void copy_demod_out(const pcs_handle* h, pcs_result* res, int32_t* sym, i
     if (sym) memcpy(sym, h->h_sym, sizeof(int) * n);
     if (centre) memcpy(centre, h->h_centre, sizeof(int) * n);
     if (mag) memcpy(mag, h->h_mag, sizeof(float) * n);
+}
+
+// ---- whole-chunk CUDA graph ------------------------------------------------------------------------------
+static bool graph_usable(const pcs_handle* h) {
+    return h->graph_enabled && !h->graph_failed && !h->profiling && h->bin_lo == 0 && h->bin_hi == h->D &&
+           h->d_x_cur == h->d_x && h->eager_chunks >= 1;
+}
+
+static int enqueue_chunk_eager(pcs_handle* h) {
+    if (int rc = enqueue_search(h)) return rc;
+    if (int rc = enqueue_demod(h, -1, false)) return rc;
+    if (int rc = enqueue_fetch_search(h)) return rc;
+    return enqueue_fetch_demod(h);
+}
+
+// search + estimate + demod + D2H of the results for the chunk in d_x, as one graph launch when possible.
+static int enqueue_chunk(pcs_handle* h) {
+    if (graph_usable(h) && !h->gexec) {
+        cudaGraph_t graph = nullptr;
+        const int64_t before = h->launches;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = enqueue_chunk_eager(h);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (rc == 0 && ce == cudaSuccess && graph &&
+                cudaGraphInstantiate(&h->gexec, graph, 0) == cudaSuccess) {
+                h->graph_launches = h->launches - before;
+            } else {
+                h->gexec = nullptr;
+                h->graph_failed = true;
+                cudaGetLastError();
+            }
+            if (graph) cudaGraphDestroy(graph);
+            h->launches = before;
+        } else {
+            h->graph_failed = true;
+            cudaGetLastError();
+        }
+    }
+    if (graph_usable(h) && h->gexec) {
+        CUDA_TRY(cudaGraphLaunch(h->gexec, h->stream));
+        h->launches += h->graph_launches;
+    } else {
+        if (int rc = enqueue_chunk_eager(h)) return rc;
+        h->eager_chunks++;
+    }
+    h->fetch_in_flight = true;
+    return 0;
 }
 
 int pcs_upload(pcs_handle* h) {
@@ -730,11 +861,9 @@ int pcs_process(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int3
     if (!h) return fail(PCS_ERR_INVALID, "null handle");
     if (!h->uploaded) return fail(PCS_ERR_STATE, "pcs_process before pcs_upload");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (int rc = enqueue_search(h)) return rc;
-    if (int rc = enqueue_demod(h, -1, false)) return rc;
-    if (int rc = enqueue_fetch_search(h)) return rc;
-    if (int rc = enqueue_fetch_demod(h)) return rc;
+    if (int rc = enqueue_chunk(h)) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->fetch_in_flight = false;
     h->searched = h->demodulated = true;
     h->h_res->demod_shift = h->h_res->shift;
     copy_search_out(h, res, E_out);
@@ -743,9 +872,22 @@ int pcs_process(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int3
 }
 
 int pcs_enqueue_device(pcs_handle* h, const void* d_chunk) {
-    if (int rc = pcs_upload_device(h, d_chunk)) return rc;
-    if (int rc = enqueue_search(h)) return rc;
-    if (int rc = enqueue_demod(h, -1, false)) return rc;
+    if (!h || !d_chunk) return fail(PCS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->graph_enabled && !h->graph_failed && !h->profiling && h->bin_lo == 0 && h->bin_hi == h->D) {
+        // graph mode: the captured kernels read the handle's own chunk buffer, so stage the chunk there (one 8N-byte
+        // device-to-device copy, ~1 us per MB)
+        CUDA_TRY(cudaMemcpyAsync(h->d_x, d_chunk, sizeof(float2) * h->N, cudaMemcpyDeviceToDevice, h->stream));
+        h->d_x_cur = h->d_x;
+        h->uploaded = true;
+        if (int rc = enqueue_spectrum(h)) return rc;
+        if (int rc = enqueue_chunk(h)) return rc;
+    } else {
+        if (int rc = pcs_upload_device(h, d_chunk)) return rc;
+        if (int rc = enqueue_search(h)) return rc;
+        if (int rc = enqueue_demod(h, -1, false)) return rc;
+        h->fetch_in_flight = false;
+    }
     h->searched = h->demodulated = true;
     return PCS_OK;
 }
@@ -754,9 +896,12 @@ int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_
     if (!h) return fail(PCS_ERR_INVALID, "null handle");
     if (!h->demodulated) return fail(PCS_ERR_STATE, "pcs_fetch before a chunk was enqueued");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (int rc = enqueue_fetch_search(h)) return rc;
-    if (int rc = enqueue_fetch_demod(h)) return rc;
+    if (!h->fetch_in_flight) {
+        if (int rc = enqueue_fetch_search(h)) return rc;
+        if (int rc = enqueue_fetch_demod(h)) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->fetch_in_flight = false;
     h->h_res->demod_shift = h->h_res->shift;
     copy_search_out(h, res, E_out);
     copy_demod_out(h, res, sym, centre, mag);
@@ -775,6 +920,10 @@ int pcs_get_spectrum(pcs_handle* h, float* X_out) {
     if (!h || !X_out) return fail(PCS_ERR_INVALID, "null argument");
     if (!h->uploaded) return fail(PCS_ERR_STATE, "no chunk uploaded");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->spectrum_full) {
+        if (int rc = fft_large<-1>(h, LoadC{h->d_x_cur}, h->d_X)) return rc;
+        h->spectrum_full = true;
+    }
     CUDA_TRY(cudaMemcpyAsync(X_out, h->d_X, sizeof(float2) * h->N, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PCS_OK;

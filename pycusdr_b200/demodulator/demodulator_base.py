@@ -35,7 +35,7 @@ SNR_WINDOW = 5              # dem_base:620
 
 class Demodulator:
 
-    def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0):
+    def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
@@ -122,7 +122,7 @@ class Demodulator:
             element_offset=self.doppIdxArrayOffset, shifts=self.doppCyperSymNorm, masks=masks,
             window_width=self.windowWidth, sum_all_masks=self.SUM_ALL_MASKS_PYTHON,
             code_search_mask_offset=self.CODE_SEARCH_MASK_OFFSET, samples_per_sym=self.spsym, path=path,
-            log2_block=log2_block, snr_window=SNR_WINDOW)
+            log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph)
         self.GPU_bufSignalTime_cpu_handle = self._engine.host_buffer
 
         # cross-call state

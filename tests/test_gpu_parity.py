@@ -264,3 +264,30 @@ def test_stx_backend_matches_oracle():
     for g, r in zip(got[1:], ref[1:]):      # chunk 0 holds the zero-filled overlap (see the stream test)
         np.testing.assert_array_equal(g["data"], r["data"])
     np.testing.assert_array_equal(dem.clippedPeakIPure, orc.clippedPeakIPure)
+
+
+def test_graph_replay_and_eager_launches_agree():
+    """The per-chunk sequence replayed as a CUDA graph must give the very same bytes as launching it kernel by kernel."""
+    conf = load_conf("benchmark/bench_GMSK.json")
+    demA, _ = _demods(conf, use_graph=True)
+    demB, _ = _demods(conf, use_graph=False)
+    sig, _ = S.bench_stream("GMSK", 12, seed=6)
+    a, b = O.run_stream(demA, sig), O.run_stream(demB, sig)
+    assert len(a) > 5
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x["data"], y["data"])
+        np.testing.assert_array_equal(x["trust"], y["trust"])
+        np.testing.assert_equal(x["doppler"], y["doppler"])
+        np.testing.assert_equal(x["doppler_std"], y["doppler_std"])
+        np.testing.assert_equal(x["SNR"], y["SNR"])
+    assert demA._engine.launch_count == demB._engine.launch_count
+
+
+def test_snr_matches_oracle_on_a_stream():
+    """computeSNR (dem_base:635-667) from the pruned spectrum bins vs the oracle's full-spectrum evaluation."""
+    conf = load_conf("benchmark/bench_GMSK.json")
+    dem, orc = _demods(conf)
+    sig, _ = S.bench_stream("GMSK", 15, seed=8)
+    for (fa, fb, _, _, _, _) in _run_both(dem, orc, sig):
+        np.testing.assert_allclose(fa[3], fb[3], rtol=2e-4, atol=2e-4, equal_nan=True)
+        np.testing.assert_allclose(fa[1], fb[1], rtol=1e-4, atol=1e-3)
