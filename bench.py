@@ -280,6 +280,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--log2-block", type=int, default=0)
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="chunks in flight for the device-resident figure (one handle + stream each; SURVEY 8(d) allows >= 2)")
     args = ap.parse_args()
 
     from pycusdr_b200.config import loadModularJson
@@ -355,35 +357,72 @@ def main():
             eng.enqueue_device(ptr)
             return eng.fetch()
         timing_stream = torch.cuda.ExternalStream(eng.stream)
+        # chunks in flight: handle k % K takes chunk k, so the latency-bound tail of one chunk (estimate, demod, timing,
+        # symbol decisions, result copies) overlaps the search kernel of the next one
+        K = max(1, args.inflight)
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block) for _ in range(K - 1)]
+        engs = [eng] + [d._engine for d in extra]
+        streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
 
     ptrs = [dev_chunks[i].data_ptr() for i in range(ring)]
     checksum = 0
-    for i in range(args.warmup):
-        res, E, sym, centre, mag = one_step(ptrs[i % ring])
-    torch.cuda.synchronize()
-    if dist is not None:
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def consume(out):
+        return int(out[0].shift) + int(out[2][:16].sum())
+
+    if world > 1:
+        for i in range(args.warmup):
+            one_step(ptrs[i % ring])
+        torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-
-    launches0 = eng.launch_count
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(timing_stream)
-    for i in range(args.steps):
-        res, E, sym, centre, mag = one_step(ptrs[(args.warmup + i) % ring])
-        checksum += int(res.shift) + int(sym[:16].sum())
-    ev1.record(timing_stream)
-    torch.cuda.synchronize()
+        launches0 = eng.launch_count
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0.record(timing_stream)
+        for i in range(args.steps):
+            checksum += consume(one_step(ptrs[(args.warmup + i) % ring]))
+        ev1.record(timing_stream)
+        torch.cuda.synchronize()
+        launches = eng.launch_count - launches0
+    else:
+        def pipeline(first, count, timed):
+            """chunk k on handle k % K; the result of chunk k - K + 1 is collected right after chunk k is enqueued."""
+            acc = 0
+            if timed:
+                ev0.record(streams[0])
+                for st in streams[1:]:
+                    st.wait_event(ev0)
+            for i in range(count):
+                e = engs[i % K]
+                if i >= K:
+                    acc += consume(e.fetch())
+                e.enqueue_device(ptrs[(first + i) % ring])
+            for i in range(count, count + min(K, count)):
+                acc += consume(engs[i % K].fetch())
+            if timed:
+                for st in streams[1:]:
+                    streams[0].wait_stream(st)
+                ev1.record(streams[0])
+            return acc
+        pipeline(0, max(args.warmup, 2 * K), False)      # also lets every handle capture its graph
+        torch.cuda.synchronize()
+        launches0 = sum(e.launch_count for e in engs)
+        sampler = ClockSampler(local)
+        sampler.start()
+        checksum = pipeline(args.warmup, args.steps, True)
+        torch.cuda.synchronize()
+        launches = sum(e.launch_count for e in engs) - launches0
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0
     if dist is not None:
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = step_samples / (ms_step * 1e-3) / 1e6
+    res = one_step(ptrs[0])[0]
 
     # ---- per-stage device times: same chunks again with CUDA events around every stage on the handle's stream
     #      (launched kernel by kernel; the timed region above replays them as one CUDA graph) ----
@@ -472,6 +511,7 @@ def main():
                    "parallelism": "single GPU" if world == 1 else f"doppler bins sharded over {world} GPUs + NCCL all-gather"},
         "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
         "launch_mode": "cuda_graph" if world == 1 else "eager + NCCL",
+        "chunks_in_flight": (K if world == 1 else 1),
         "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum,
     }
     print(json.dumps(line))

@@ -75,7 +75,7 @@ typedef struct {
     int32_t peak_bin, peak_mask, peak_offset;
     int32_t sig_start, sig_len, noise_start, noise_len; /* circular spectrum windows for computeSNR */
     int32_t demod_shift; /* the shift the demod stage used */
-    int32_t pad_;
+    int32_t xchg_timeout;/* 1 = a peer's rows never arrived (pcs_enqueue_owner_tail) */
 } pcs_result;
 
 typedef struct pcs_handle pcs_handle;
@@ -167,6 +167,20 @@ int pcs_set_bin_range(pcs_handle* h, int32_t lo, int32_t hi);
 int pcs_shard_buffers(pcs_handle* h, void** d_energy, void** d_peak_val, void** d_peak_off);
 int pcs_enqueue_search_local(pcs_handle* h);
 int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod);
+
+/* The same sharding without NCCL on the data path: the exchange goes through NVLink peer memory.  Every rank
+ * exports one small exchange region (2 x three [D*M] tables + arrival flags) with CUDA IPC (pcs_peer_export, 64-byte
+ * handle), the host all-gathers the handles once (any transport) and attaches them (pcs_peer_attach).  Per chunk
+ * `seq`, every rank calls pcs_enqueue_search_push(seq, owner): its search / reduction kernels store their rows of the
+ * tables directly into the OWNER's region (P2P stores) and a flag kernel publishes the arrival.  Only the owner calls
+ * pcs_enqueue_owner_tail(seq): a wait kernel acquires all flags, then estimate + demod + result copies run on the
+ * gathered table (identical to the single-GPU table), and pcs_fetch collects them.  Owners rotate (seq % world), so
+ * the non-sharded tail costs each rank 1/world of a chunk.  Regions are double-buffered by (seq / world) parity; a
+ * rank must enqueue chunks in increasing seq order. */
+int pcs_peer_export(pcs_handle* h, void* ipc_handle_out /* 64 bytes */);
+int pcs_peer_attach(pcs_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
+int pcs_enqueue_search_push(pcs_handle* h, int64_t seq, int32_t owner);
+int pcs_enqueue_owner_tail(pcs_handle* h, int64_t seq);
 
 /* Make the handle enqueue on a caller-owned stream (cudaStream_t as an integer), e.g. the framework
  * stream NCCL collectives are ordered on.  The handle's own stream is destroyed. */

@@ -37,7 +37,7 @@ class Result(C.Structure):
         ("shift", C.c_int32), ("status", C.c_int32), ("timing", C.c_float * 3), ("n_sym", C.c_int32),
         ("sp_sym", C.c_double), ("code_offset", C.c_double), ("peak_val", C.c_float), ("peak_bin", C.c_int32),
         ("peak_mask", C.c_int32), ("peak_offset", C.c_int32), ("sig_start", C.c_int32), ("sig_len", C.c_int32),
-        ("noise_start", C.c_int32), ("noise_len", C.c_int32), ("demod_shift", C.c_int32), ("pad_", C.c_int32)]
+        ("noise_start", C.c_int32), ("noise_len", C.c_int32), ("demod_shift", C.c_int32), ("xchg_timeout", C.c_int32)]
 
 
 class PlanInfo(C.Structure):
@@ -72,6 +72,10 @@ SYMBOLS = {
     "pcs_shard_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "pcs_enqueue_search_local": (C.c_int, [_P]),
     "pcs_enqueue_estimate_and_demod": (C.c_int, [_P, C.c_int32]),
+    "pcs_peer_export": (C.c_int, [_P, _P]),
+    "pcs_peer_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "pcs_enqueue_search_push": (C.c_int, [_P, C.c_int64, C.c_int32]),
+    "pcs_enqueue_owner_tail": (C.c_int, [_P, C.c_int64]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -242,6 +246,25 @@ class Engine:
 
     def enqueue_estimate_and_demod(self, with_demod=True):
         self._check(self.lib.pcs_enqueue_estimate_and_demod(self._h, int(bool(with_demod))))
+
+    # -- bin sharding over NVLink peer memory ------------------------------------------------------
+    def peer_export(self):
+        """64-byte CUDA IPC handle of this handle's exchange region."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.pcs_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, rank, world, handles):
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise ValueError("need one 64-byte IPC handle per rank")
+        self._check(self.lib.pcs_peer_attach(self._h, int(rank), int(world), C.c_char_p(blob)))
+
+    def enqueue_search_push(self, seq, owner):
+        self._check(self.lib.pcs_enqueue_search_push(self._h, int(seq), int(owner)))
+
+    def enqueue_owner_tail(self, seq):
+        self._check(self.lib.pcs_enqueue_owner_tail(self._h, int(seq)))
 
     def set_stream(self, stream_ptr):
         self._check(self.lib.pcs_set_stream(self._h, int(stream_ptr)))

@@ -24,10 +24,17 @@ namespace pcs {
 PCS_DEVINL int padi(int i) { return i + (i >> 4); }
 constexpr int padded_len(int n) { return n + (n >> 4); }
 
-PCS_DEVINL float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-PCS_DEVINL float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on Blackwell's packed fp32x2 pipe forms (FADD2 / FMUL2 / FFMA2, sm_100+): one instruction per
+// complex add, subtract or +-i rotation (the swap and per-component negation are operand modifiers in SASS:
+// "FADD2 R2, R2.F32x2.HI_LO, -R4.F32x2.LO_HI.NP"), three instead of four per complex multiply.  Every component
+// is still an IEEE round-to-nearest add / fma, so results are bit-identical to the scalar formulation; what the
+// packed forms buy is issue slots (a packed instruction occupies the FMA pipe for two slots but the scheduler for
+// one; measured: tools/ubench/fp32x2.cu).
+PCS_DEVINL float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+PCS_DEVINL float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 PCS_DEVINL float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = fma2(a.x, b, (-a.y b.y, a.y b.x)); same roundings as two scalar fmas
+    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-a.y * b.y, a.y * b.x));
 }
 PCS_DEVINL float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // |z|^2 with the contraction nvcc applies to the reference's ComplexAbsSquared (FMUL + FFMA).
@@ -36,13 +43,27 @@ PCS_DEVINL float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
 // multiply by exp(i*DIR*theta) given c = cos(theta), s = sin(theta)
 template <int DIR>
 PCS_DEVINL float2 mulw(float2 v, float c, float s) {
-    if (DIR < 0) return make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
-    return make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.y, c, v.x * s));
+    if (DIR < 0) return __ffma2_rn(v, make_float2(c, c), make_float2(v.y * s, -v.x * s));
+    return __ffma2_rn(v, make_float2(c, c), make_float2(-v.y * s, v.x * s));
 }
 // multiply by DIR*i
 template <int DIR>
 PCS_DEVINL float2 muli(float2 v) {
     return DIR < 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
+}
+// a + DIR*i*b and a - DIR*i*b (one FADD2 each)
+template <int DIR>
+PCS_DEVINL float2 caddi(float2 a, float2 b) { return __fadd2_rn(a, muli<DIR>(b)); }
+template <int DIR>
+PCS_DEVINL float2 csubi(float2 a, float2 b) { return __fadd2_rn(a, muli<-DIR>(b)); }
+// v * (1 + DIR*i) / sqrt(2) and v * (-1 + DIR*i) / sqrt(2)
+template <int DIR>
+PCS_DEVINL float2 mulw8_1(float2 v) {
+    return __fmul2_rn(caddi<DIR>(v, v), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+}
+template <int DIR>
+PCS_DEVINL float2 mulw8_3(float2 v) {
+    return __fmul2_rn(csub(muli<DIR>(v), v), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
 }
 
 PCS_DEVINL void dft2(float2& a, float2& b) {
@@ -53,11 +74,11 @@ PCS_DEVINL void dft2(float2& a, float2& b) {
 
 template <int DIR>
 PCS_DEVINL void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = muli<DIR>(csub(a1, a3));
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
-    a1 = cadd(t1, t3);
-    a3 = csub(t1, t3);
+    a1 = caddi<DIR>(t1, t3);
+    a3 = csubi<DIR>(t1, t3);
 }
 
 #define PCS_SQRT1_2 0.70710678118654752440f
@@ -89,15 +110,9 @@ struct Dft<8, DIR> {
 #pragma unroll
         for (int r2 = 0; r2 < 4; ++r2) dft2(v[r2], v[4 + r2]);
         // slot 4 + r2 *= W8^{r2}
-        {
-            float2 t = v[5];  // W8^1 = (1 + DIR*i)/sqrt2
-            v[5] = DIR < 0 ? make_float2((t.x + t.y) * PCS_SQRT1_2, (t.y - t.x) * PCS_SQRT1_2)
-                           : make_float2((t.x - t.y) * PCS_SQRT1_2, (t.y + t.x) * PCS_SQRT1_2);
-            v[6] = muli<DIR>(v[6]);  // W8^2 = DIR*i
-            t = v[7];                // W8^3 = (-1 + DIR*i)/sqrt2
-            v[7] = DIR < 0 ? make_float2((t.y - t.x) * PCS_SQRT1_2, (-t.x - t.y) * PCS_SQRT1_2)
-                           : make_float2((-t.x - t.y) * PCS_SQRT1_2, (t.x - t.y) * PCS_SQRT1_2);
-        }
+        v[5] = mulw8_1<DIR>(v[5]);   // W8^1 = (1 + DIR*i)/sqrt2
+        v[6] = muli<DIR>(v[6]);      // W8^2 = DIR*i
+        v[7] = mulw8_3<DIR>(v[7]);   // W8^3 = (-1 + DIR*i)/sqrt2
         dft4<DIR>(v[0], v[1], v[2], v[3]);
         dft4<DIR>(v[4], v[5], v[6], v[7]);
     }
@@ -110,13 +125,13 @@ struct Dft<16, DIR> {
         for (int r2 = 0; r2 < 4; ++r2) dft4<DIR>(v[r2], v[4 + r2], v[8 + r2], v[12 + r2]);
         // slot 4*q1 + r2 *= W16^{q1*r2}
         v[5] = mulw<DIR>(v[5], PCS_COS_PI_8, PCS_SIN_PI_8);     // W16^1
-        v[6] = mulw<DIR>(v[6], PCS_SQRT1_2, PCS_SQRT1_2);       // W16^2
+        v[6] = mulw8_1<DIR>(v[6]);                              // W16^2
         v[7] = mulw<DIR>(v[7], PCS_SIN_PI_8, PCS_COS_PI_8);     // W16^3
-        v[9] = mulw<DIR>(v[9], PCS_SQRT1_2, PCS_SQRT1_2);       // W16^2
+        v[9] = mulw8_1<DIR>(v[9]);                              // W16^2
         v[10] = muli<DIR>(v[10]);                               // W16^4
-        v[11] = mulw<DIR>(v[11], -PCS_SQRT1_2, PCS_SQRT1_2);    // W16^6
+        v[11] = mulw8_3<DIR>(v[11]);                            // W16^6
         v[13] = mulw<DIR>(v[13], PCS_SIN_PI_8, PCS_COS_PI_8);   // W16^3
-        v[14] = mulw<DIR>(v[14], -PCS_SQRT1_2, PCS_SQRT1_2);    // W16^6
+        v[14] = mulw8_3<DIR>(v[14]);                            // W16^6
         v[15] = mulw<DIR>(v[15], -PCS_COS_PI_8, -PCS_SIN_PI_8); // W16^9
 #pragma unroll
         for (int q1 = 0; q1 < 4; ++q1) dft4<DIR>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);

@@ -29,7 +29,7 @@ struct DevResult {
     int peak_bin, peak_mask, peak_offset;
     int sig_start, sig_len, noise_start, noise_len;   // circular windows of X gathered for computeSNR
     int demod_shift;     // shift actually used by the demod stage
-    int pad_;
+    int xchg_timeout;    // 1 = a peer's rows never arrived (bin sharding over peer memory)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -195,8 +195,8 @@ struct Os256Params {
     float invN;
 };
 
-PCS_DEVINL float2 cmulc(float2 a, float2 b) {   // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+PCS_DEVINL float2 cmulc(float2 a, float2 b) {   // a * conj(b) = fma2(a, b.x, (a.y b.y, -a.x b.y))
+    return __ffma2_rn(a, make_float2(b.x, b.x), make_float2(a.y * b.y, -a.x * b.y));
 }
 
 // 256-point transform of one 16-lane group. In: v[r] = in[t + 16 r]. Out: slot s holds out[t + 16 dft_q<16>(s)].
@@ -950,6 +950,35 @@ __global__ void centres_kernel(const float* __restrict__ ymag, const DevResult* 
         out_idx[x] = (int)__fadd_rn(__fadd_rn(tbase, (float)maxCentreIdx), (float)offsetComp);
         out_mag[x] = maxVal;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer exchange (bin sharding over NVLink): arrival flags in the owner's exchange region.
+// ---------------------------------------------------------------------------------------------
+__global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {
+    // the rows were stored by the preceding kernels of this stream; make them visible system-wide, then publish
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+// One lane per peer spins (with back-off) until that peer's flag reaches `want`; gives up after ~2 s and marks the
+// result block (status 2) instead of hanging the GPU if a peer died.
+__global__ void peer_wait_kernel(const unsigned long long* flags, int world, unsigned long long want, DevResult* res) {
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+            if (v >= want) break;
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            __nanosleep(200);
+        }
+    }
+    const unsigned all_ok = __all_sync(0xffffffffu, ok);
+    if (r == 0) res->xchg_timeout = all_ok ? 0 : 1;
+    __threadfence_system();
 }
 
 // fp32 FMA peak probe: 16 independent FMA chains per thread.

@@ -92,6 +92,18 @@ struct pcs_handle {
     bool graph_enabled = true, graph_failed = false, fetch_in_flight = false;
     int eager_chunks = 0;
     int64_t graph_launches = 0;
+    // bin-sharded search over NVLink peer memory (one process per GPU): exchange region = 2 x {E, peak value,
+    // peak offset}[D*M] + 2 x PCS_MAX_PEERS arrival flags, exported with CUDA IPC and written by the peers' kernels
+    unsigned char* d_xchg = nullptr;
+    size_t xchg_bytes = 0;
+    unsigned char* peer_base[16] = {};
+    int peer_rank = 0, peer_world = 0;
+    bool peers_attached = false;
+    float *tab_E = nullptr, *tab_pv = nullptr;   // tables the search stage writes / the estimate stage reads
+    int* tab_po = nullptr;
+    cudaStream_t side = nullptr;       // forked branch of the graph: chunk spectrum -> SNR bins (off the critical path)
+    cudaEvent_t ev_fork = nullptr, ev_est = nullptr, ev_side = nullptr;
+    bool spectrum_pending = false;     // pass 1 of the chunk spectrum not enqueued yet for the current upload
     int bin_lo = 0, bin_hi = 0;        // Doppler rows this handle searches (bin sharding); default all
     int win_cap = PCS_WINDOW_MAX;      // largest computeSNR window this Doppler grid can produce
     int64_t launches = 0;
@@ -416,7 +428,13 @@ int pcs_destroy(pcs_handle* h) {
     void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
+    for (int r = 0; r < h->peer_world; ++r)
+        if (h->peer_base[r] && r != h->peer_rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->d_xchg) cudaFree(h->d_xchg);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->side) cudaStreamDestroy(h->side);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_est, h->ev_side})
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -448,6 +466,10 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (prop.major < 10) return fail(PCS_ERR_NO_DEVICE, "device %s is sm_%d%d; this build targets sm_100a only", prop.name, prop.major, prop.minor);
     h->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_est, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     h->N = N;
     h->logN = ilog2(N);
     h->logN1 = h->logN / 2;
@@ -483,6 +505,7 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (int rc = dev_alloc(h, &h->d_E, (size_t)D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_peakv, (size_t)D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_peako, (size_t)D * M)) return rc;
+    h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
     if (int rc = dev_alloc(h, &h->d_ymag, (size_t)M * N)) return rc;
     if (int rc = dev_alloc(h, &h->d_p, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_sym, (size_t)h->max_sym)) return rc;
@@ -614,7 +637,7 @@ static int enqueue_search_local256(pcs_handle* h) {
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_part_sum, h->d_part_max, h->d_part_blk,
-                                                                  h->d_Efull + row0, h->d_peakv + row0, h->d_peako + row0);
+                                                                  h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -639,8 +662,8 @@ static int enqueue_search_local(pcs_handle* h) {
     StageTimer t2(h, PCS_STAGE_REDUCE);
     const int DM = Dl * h->M;
     search_reduce_kernel<<<(DM * 32 + 255) / 256, 256, 0, h->stream>>>(p.psum, p.pmax, p.pidx, DM, h->nblk,
-                                                                        h->d_Efull + row0, h->d_peakv + row0,
-                                                                        h->d_peako + row0);
+                                                                        h->tab_E + row0, h->tab_pv + row0,
+                                                                        h->tab_po + row0);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -653,16 +676,19 @@ static int enqueue_search(pcs_handle* h) {
 
 // findDopplerEst + shift interpolation + peak + SNR windows over the full [D][M] energy table (which, with bin
 // sharding, the caller has all-gathered into d_Efull / d_peakv / d_peako beforehand).
-static int enqueue_estimate(pcs_handle* h) {
-    StageTimer t2(h, PCS_STAGE_ESTIMATE);
+static int enqueue_estimate_kernel(pcs_handle* h) {
     EstimateParams e{};
-    e.Efull = h->d_Efull; e.E = h->d_E; e.peak_val = h->d_peakv; e.peak_off = h->d_peako; e.shifts = h->d_shifts;
+    e.Efull = h->tab_E; e.E = h->d_E; e.peak_val = h->tab_pv; e.peak_off = h->tab_po; e.shifts = h->d_shifts;
     e.res = h->d_res;
     e.D = h->D; e.M = h->M; e.N = h->N; e.num_dopplers = h->cfg.num_dopplers; e.element_offset = h->cfg.element_offset;
     e.sum_all = h->cfg.sum_all_masks ? 1 : 0; e.window_width = h->cfg.snr_window; e.window_cap = h->win_cap;
     estimate_kernel<<<1, 256, 0, h->stream>>>(e);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_snr_bins(pcs_handle* h) {
     const float2* tw2 = nullptr;
     if (int rc = get_twiddles(h, h->logN2, &tw2)) return rc;
     spectrum_bins_kernel<<<(2 * h->win_cap + 7) / 8, 256, 0, h->stream>>>(h->d_scratch, tw2, 1 << h->logN1, 1 << h->logN2,
@@ -670,6 +696,16 @@ static int enqueue_estimate(pcs_handle* h) {
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+static int enqueue_estimate(pcs_handle* h) {
+    if (h->spectrum_pending) {
+        if (int rc = enqueue_spectrum(h)) return rc;
+        h->spectrum_pending = false;
+    }
+    StageTimer t2(h, PCS_STAGE_ESTIMATE);
+    if (int rc = enqueue_estimate_kernel(h)) return rc;
+    return enqueue_snr_bins(h);
 }
 
 static int enqueue_timing_spectrum(pcs_handle* h) {
@@ -733,9 +769,13 @@ static int enqueue_demod(pcs_handle* h, int shift, bool want_complex) {
     return 0;
 }
 
+static int enqueue_fetch_windows(pcs_handle* h);
 static int enqueue_fetch_search(pcs_handle* h) {
     CUDA_TRY(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_E, h->d_E, sizeof(float) * h->D * h->M, cudaMemcpyDeviceToHost, h->stream));
+    return enqueue_fetch_windows(h);
+}
+static int enqueue_fetch_windows(pcs_handle* h) {
     CUDA_TRY(cudaMemcpyAsync(h->h_sigwin, h->d_sigwin, sizeof(float2) * h->win_cap, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_noisewin, h->d_noisewin, sizeof(float2) * h->win_cap, cudaMemcpyDeviceToHost, h->stream));
     return 0;
@@ -777,13 +817,41 @@ static int enqueue_chunk_eager(pcs_handle* h) {
     return enqueue_fetch_demod(h);
 }
 
+// The same work as enqueue_chunk_eager shaped as a fork-join for capture: the chunk spectrum (pass 1) and, once the
+// estimate is known, the SNR bins and their D2H run on a side branch; the main branch goes search -> estimate ->
+// demod -> timing -> symbols -> D2H without waiting for them.
+static int enqueue_chunk_forked(pcs_handle* h) {
+    cudaStream_t main_s = h->stream;
+    CUDA_TRY(cudaEventRecord(h->ev_fork, main_s));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    h->stream = h->side;
+    int rc = enqueue_spectrum(h);
+    h->stream = main_s;
+    if (rc) return rc;
+    if ((rc = enqueue_search_local(h))) return rc;
+    if ((rc = enqueue_estimate_kernel(h))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_est, main_s));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_est, 0));
+    h->stream = h->side;
+    rc = enqueue_snr_bins(h);
+    if (!rc) rc = enqueue_fetch_windows(h);
+    h->stream = main_s;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_side, h->side));
+    if ((rc = enqueue_demod(h, -1, false))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->h_E, h->d_E, sizeof(float) * h->D * h->M, cudaMemcpyDeviceToHost, main_s));
+    if ((rc = enqueue_fetch_demod(h))) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(main_s, h->ev_side, 0));
+    return 0;
+}
+
 // search + estimate + demod + D2H of the results for the chunk in d_x, as one graph launch when possible.
 static int enqueue_chunk(pcs_handle* h) {
     if (graph_usable(h) && !h->gexec) {
         cudaGraph_t graph = nullptr;
         const int64_t before = h->launches;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int rc = enqueue_chunk_eager(h);
+            const int rc = enqueue_chunk_forked(h);
             const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             if (rc == 0 && ce == cudaSuccess && graph &&
                 cudaGraphInstantiate(&h->gexec, graph, 0) == cudaSuccess) {
@@ -803,6 +871,7 @@ static int enqueue_chunk(pcs_handle* h) {
     if (graph_usable(h) && h->gexec) {
         CUDA_TRY(cudaGraphLaunch(h->gexec, h->stream));
         h->launches += h->graph_launches;
+        h->spectrum_pending = false;
     } else {
         if (int rc = enqueue_chunk_eager(h)) return rc;
         h->eager_chunks++;
@@ -818,7 +887,9 @@ int pcs_upload(pcs_handle* h) {
     h->d_x_cur = h->d_x;
     h->uploaded = true;
     h->searched = h->demodulated = false;
-    return enqueue_spectrum(h);
+    h->spectrum_pending = true;        // enqueued with the estimate (eager) or on the graph's side branch
+    h->spectrum_full = false;
+    return PCS_OK;
 }
 
 int pcs_upload_device(pcs_handle* h, const void* d_chunk) {
@@ -827,7 +898,9 @@ int pcs_upload_device(pcs_handle* h, const void* d_chunk) {
     h->d_x_cur = reinterpret_cast<const float2*>(d_chunk);
     h->uploaded = true;
     h->searched = h->demodulated = false;
-    return enqueue_spectrum(h);
+    h->spectrum_pending = true;
+    h->spectrum_full = false;
+    return PCS_OK;
 }
 
 int pcs_search(pcs_handle* h, pcs_result* res, float* E_out) {
@@ -880,7 +953,8 @@ int pcs_enqueue_device(pcs_handle* h, const void* d_chunk) {
         CUDA_TRY(cudaMemcpyAsync(h->d_x, d_chunk, sizeof(float2) * h->N, cudaMemcpyDeviceToDevice, h->stream));
         h->d_x_cur = h->d_x;
         h->uploaded = true;
-        if (int rc = enqueue_spectrum(h)) return rc;
+        h->spectrum_pending = true;
+        h->spectrum_full = false;
         if (int rc = enqueue_chunk(h)) return rc;
     } else {
         if (int rc = pcs_upload_device(h, d_chunk)) return rc;
@@ -1071,6 +1145,100 @@ int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod) {
         if (int rc = enqueue_demod(h, -1, false)) return rc;
         h->demodulated = true;
     }
+    return PCS_OK;
+}
+
+// ---- bin sharding over NVLink peer memory ------------------------------------------------------------------------
+static size_t xchg_table_bytes(const pcs_handle* h) { return (size_t)h->D * h->M * 4; }
+static size_t xchg_flags_offset(const pcs_handle* h) { return (6 * xchg_table_bytes(h) + 255) / 256 * 256; }
+static float* xchg_table(const pcs_handle* h, unsigned char* base, int parity, int k) {
+    return reinterpret_cast<float*>(base + (size_t)(parity * 3 + k) * xchg_table_bytes(h));
+}
+static unsigned long long* xchg_flags(const pcs_handle* h, unsigned char* base, int parity) {
+    return reinterpret_cast<unsigned long long*>(base + xchg_flags_offset(h)) + parity * 16;
+}
+
+int pcs_peer_export(pcs_handle* h, void* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return fail(PCS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->d_xchg) {
+        h->xchg_bytes = xchg_flags_offset(h) + 2 * 16 * sizeof(unsigned long long);
+        CUDA_TRY(cudaMalloc((void**)&h->d_xchg, h->xchg_bytes));      // plain cudaMalloc: CUDA IPC cannot export pooled memory
+        CUDA_TRY(cudaMemset(h->d_xchg, 0, h->xchg_bytes));
+        h->dev_bytes += (int64_t)h->xchg_bytes;
+    }
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    return PCS_OK;
+}
+
+int pcs_peer_attach(pcs_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
+    if (!h || !ipc_handles) return fail(PCS_ERR_INVALID, "null argument");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(PCS_ERR_INVALID, "bad rank %d / world %d", rank, world);
+    if (!h->d_xchg) return fail(PCS_ERR_STATE, "pcs_peer_attach before pcs_peer_export");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const unsigned char* hs = reinterpret_cast<const unsigned char*>(ipc_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->peer_base[r] = h->d_xchg; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, hs + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[r] = reinterpret_cast<unsigned char*>(p);
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    h->peers_attached = true;
+    return PCS_OK;
+}
+
+int pcs_enqueue_search_push(pcs_handle* h, int64_t seq, int32_t owner) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->peers_attached) return fail(PCS_ERR_STATE, "pcs_enqueue_search_push before pcs_peer_attach");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "search before upload");
+    if (owner < 0 || owner >= h->peer_world || seq < 0) return fail(PCS_ERR_INVALID, "bad owner %d / seq %lld", owner, (long long)seq);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int parity = (int)((seq / h->peer_world) & 1);
+    unsigned char* base = h->peer_base[owner];
+    // the search stage stores its rows of the three tables straight into the owner's exchange region (NVLink P2P
+    // stores when the owner is another GPU) ...
+    h->tab_E = xchg_table(h, base, parity, 0);
+    h->tab_pv = xchg_table(h, base, parity, 1);
+    h->tab_po = reinterpret_cast<int*>(xchg_table(h, base, parity, 2));
+    const int rc = enqueue_search_local(h);
+    h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
+    if (rc) return rc;
+    // ... and then raises its arrival flag there (system-scope release after the kernel boundary)
+    peer_flag_kernel<<<1, 1, 0, h->stream>>>(xchg_flags(h, base, parity) + h->peer_rank, (unsigned long long)seq + 1ull);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PCS_OK;
+}
+
+int pcs_enqueue_owner_tail(pcs_handle* h, int64_t seq) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->peers_attached) return fail(PCS_ERR_STATE, "pcs_enqueue_owner_tail before pcs_peer_attach");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "tail before upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int parity = (int)((seq / h->peer_world) & 1);
+    peer_wait_kernel<<<1, 32, 0, h->stream>>>(xchg_flags(h, h->d_xchg, parity), h->peer_world, (unsigned long long)seq + 1ull,
+                                              h->d_res);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->tab_E = xchg_table(h, h->d_xchg, parity, 0);
+    h->tab_pv = xchg_table(h, h->d_xchg, parity, 1);
+    h->tab_po = reinterpret_cast<int*>(xchg_table(h, h->d_xchg, parity, 2));
+    int rc = enqueue_estimate(h);
+    h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
+    if (rc) return rc;
+    h->searched = true;
+    if ((rc = enqueue_demod(h, -1, false))) return rc;
+    h->demodulated = true;
+    if ((rc = enqueue_fetch_search(h))) return rc;
+    if ((rc = enqueue_fetch_demod(h))) return rc;
+    h->fetch_in_flight = true;
     return PCS_OK;
 }
 

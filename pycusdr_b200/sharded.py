@@ -1,0 +1,94 @@
+"""Doppler-bin sharding of the search across GPUs, one process per GPU.
+
+Every rank holds the chunk and the full shift table and searches a contiguous slice of the Doppler bins.  The
+three per-(bin, mask) tables of the slice (energy, peak value, peak offset) are stored by the search kernels
+directly into the exchange region of the chunk's *owner* rank over NVLink peer memory
+(``pcs_enqueue_search_push``); the owner alone then runs the tail of the chunk -- Doppler estimate, demodulation at
+the selected bin, timing recovery, symbol decisions -- on the gathered table, which is the very table a single GPU
+would have produced, so the results are bit-identical to the unsharded path.  Owners rotate round-robin over the
+chunks, so the part of the work that does not shard costs each rank 1/world of a chunk, and no collective is on
+the per-chunk path.  ``torch.distributed`` (any backend) is used once, to exchange the 64-byte CUDA IPC handles,
+and at the end to gather the per-chunk results on rank 0.
+
+The classes here are host logic only: they drive an *engine* object with the interface of
+``pycusdr_b200._native.Engine`` (``set_bin_range``, ``peer_export``, ``peer_attach``, ``upload_device``,
+``enqueue_search_push``, ``enqueue_owner_tail``, ``fetch``), which is what lets the world_size-2 ``gloo`` test in
+``tests/test_sharded_cpu.py`` run them without a GPU.
+"""
+from collections import deque
+
+
+def bin_partition(num_bins, world):
+    """Contiguous, balanced slices ``[(lo, hi), ...]`` of ``range(num_bins)``, one per rank, none empty."""
+    if world < 1 or num_bins < world:
+        raise ValueError(f"cannot shard {num_bins} Doppler bins over {world} ranks")
+    base, extra = divmod(num_bins, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def owner_of(seq, world):
+    """Rank that runs the non-sharded tail (estimate + demod) of chunk ``seq``."""
+    return seq % world
+
+
+class ShardedSearch:
+    """Per-rank driver. ``all_gather`` is a callable ``obj -> [obj of rank 0, obj of rank 1, ...]`` (e.g. a thin
+    wrapper over ``torch.distributed.all_gather_object``)."""
+
+    def __init__(self, engine, rank, world, all_gather):
+        self.engine, self.rank, self.world = engine, rank, world
+        self.slices = bin_partition(engine.D, world)
+        lo, hi = self.slices[rank]
+        engine.set_bin_range(lo, hi)
+        handles = all_gather(engine.peer_export())
+        if len(handles) != world:
+            raise RuntimeError("handle exchange returned %d entries for %d ranks" % (len(handles), world))
+        engine.peer_attach(rank, world, handles)
+        self._owned = deque()          # chunks whose tail this rank has enqueued but not collected yet
+        self.results = {}              # seq -> whatever ``collect`` made of engine.fetch()
+        self._next_seq = 0
+
+    def enqueue(self, seq, chunk, collect=None):
+        """Enqueue chunk ``seq`` (device pointer / array understood by the engine). Chunks must come in order.
+        If this rank owns the chunk its tail is enqueued too; the results of the previously owned chunk are collected
+        first (the engine has one result staging area), through ``collect(fetch_tuple)`` if given."""
+        if seq != self._next_seq:
+            raise ValueError(f"chunks must be enqueued in order: expected {self._next_seq}, got {seq}")
+        self._next_seq += 1
+        owner = owner_of(seq, self.world)
+        if owner == self.rank:
+            self.drain(collect)
+        self.engine.upload_device(chunk)
+        self.engine.enqueue_search_push(seq, owner)
+        if owner == self.rank:
+            self.engine.enqueue_owner_tail(seq)
+            self._owned.append(seq)
+        return owner
+
+    def drain(self, collect=None):
+        """Collect the results of every owned chunk still in flight (synchronises with the device)."""
+        while self._owned:
+            seq = self._owned.popleft()
+            out = self.engine.fetch()
+            self.results[seq] = collect(out) if collect is not None else out
+        return self.results
+
+
+def gather_results(results, world, gather_object, rank):
+    """Merge the per-rank ``{seq: result}`` dicts on rank 0, ordered by chunk. ``gather_object(obj)`` returns the
+    list of all ranks' objects on rank 0 (``None`` elsewhere)."""
+    parts = gather_object(results)
+    if rank != 0:
+        return None
+    merged = {}
+    for part in parts:
+        for seq, r in part.items():
+            if seq in merged:
+                raise RuntimeError(f"chunk {seq} reported by two ranks")
+            merged[seq] = r
+    return [merged[s] for s in sorted(merged)]
