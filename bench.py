@@ -280,6 +280,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--log2-block", type=int, default=0)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=2,
                     help="chunks in flight for the device-resident figure (one handle + stream each; SURVEY 8(d) allows >= 2)")
     args = ap.parse_args()
@@ -324,7 +326,19 @@ def main():
     plan = eng.plan()
     S_nom = N // cr["samplesPerSym"]
 
-    if world > 1:   # bin sharding: this rank searches rows [lo, hi)
+    sh = None
+    if world > 1 and args.exchange == "p2p":
+        # bin sharding, exchange through NVLink peer memory, owner-only tail (pycusdr_b200/sharded.py)
+        from pycusdr_b200 import sharded
+
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        sh = sharded.ShardedSearch(eng, rank, world, all_gather)
+        lo, hi = sh.slices[rank]
+        timing_stream = torch.cuda.ExternalStream(eng.stream)
+    elif world > 1:   # bin sharding with NCCL all-gathers and a replicated tail (comparison variant)
         per = (D + world - 1) // world
         lo, hi = min(rank * per, D), min((rank + 1) * per, D)
         eng.set_bin_range(lo, max(hi, lo + 1))
@@ -371,7 +385,29 @@ def main():
     def consume(out):
         return int(out[0].shift) + int(out[2][:16].sum())
 
-    if world > 1:
+    if sh is not None:
+        warm = -(-max(args.warmup, world) // world) * world        # whole owner rounds
+        for i in range(warm):
+            sh.enqueue(i, ptrs[i % ring], collect=consume)
+        sh.drain(consume)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = eng.launch_count
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0.record(timing_stream)
+        for i in range(args.steps):
+            sh.enqueue(warm + i, ptrs[(warm + i) % ring], collect=consume)
+        sh.drain(consume)
+        ev1.record(timing_stream)
+        torch.cuda.synchronize()
+        launches = eng.launch_count - launches0
+        checksum = sum(v for k, v in sh.results.items() if k >= warm)
+        ck = torch.tensor([checksum], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ck)
+        checksum = int(ck.item())
+    elif world > 1:
         for i in range(args.warmup):
             one_step(ptrs[i % ring])
         torch.cuda.synchronize()
@@ -422,13 +458,20 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = step_samples / (ms_step * 1e-3) / 1e6
-    res = one_step(ptrs[0])[0]
+    if sh is None:
+        res = one_step(ptrs[0])[0]
 
     # ---- per-stage device times: same chunks again with CUDA events around every stage on the handle's stream
     #      (launched kernel by kernel; the timed region above replays them as one CUDA graph) ----
     eng.set_profiling(True)
-    for i in range(min(args.steps, 100)):
-        one_step(ptrs[(args.warmup + i) % ring])
+    if sh is not None:
+        base = warm + args.steps
+        for i in range(world * max(4, min(args.steps, 64) // world)):
+            sh.enqueue(base + i, ptrs[(base + i) % ring], collect=consume)
+        sh.drain(consume)
+    else:
+        for i in range(min(args.steps, 100)):
+            one_step(ptrs[(args.warmup + i) % ring])
     torch.cuda.synchronize()
     prof = eng.profile()
     eng.set_profiling(False)
@@ -508,9 +551,12 @@ def main():
                    "path": {1: "overlap_save", 2: "full", 3: "parseval"}.get(plan["path"]),
                    "block": 2 ** plan["log2_block"], "valid_per_block": plan["valid_per_block"],
                    "l2": f"ring of {ring} distinct chunks = {ring_bytes >> 20} MiB (> 126 MiB L2), one per step",
-                   "parallelism": "single GPU" if world == 1 else f"doppler bins sharded over {world} GPUs + NCCL all-gather"},
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"doppler bins sharded over {world} GPUs, rows pushed to the chunk's owner over NVLink peer memory, "
+                       f"owner-only tail, owners round-robin" if sh is not None else
+                       f"doppler bins sharded over {world} GPUs + NCCL all-gather, replicated tail")},
         "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-        "launch_mode": "cuda_graph" if world == 1 else "eager + NCCL",
+        "launch_mode": "cuda_graph" if world == 1 else ("eager, NVLink peer stores" if sh is not None else "eager + NCCL"),
         "chunks_in_flight": (K if world == 1 else 1),
         "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum,
     }

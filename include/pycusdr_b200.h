@@ -197,6 +197,30 @@ int pcs_get_profile(pcs_handle* h, double* stage_ms, int64_t* stage_count);
  * kernels; 16 independent FMA chains per thread, best of 4 timed launches). */
 int pcs_measure_fp32_peak(int device, double* tflops);
 
+/* Host-side bit post-processing of a chunk in C++ (no device work): replaces the NumPy code the reference runs after
+ * cudaFindCentres -- extractBits / extractBitsNRZs (dem_base:1012-1051), checkSymbolOverlap (dem_base:863-988), the
+ * clipped-peak tagging of the trust (dem_base:817-837) and the uint8 casts of the return statement (dem_base:859).
+ * The stitcher keeps the cross-chunk state (poswinP / posSymEnd, dem_base:977-979).  Exactly one of bit_lut
+ * (uint8[num_symbols], protocol.get_symbolLUT2()[0]) and symbol_lut (int32[num_symbols][2][lut_k], the NRZ-S table)
+ * is given.  Outputs hold at most n_sym entries; *n_out are valid. */
+typedef struct pcs_stitcher pcs_stitcher;
+typedef struct {
+    int32_t nfft;             /* 2**blockSize                                   dem_base:89 */
+    int32_t overlap;          /* 2**overlap samples                             dem_base:90 */
+    int32_t overlap_offset;   /* symbol_check_overlap_offset                    dem_base:97 */
+    int32_t error_threshold;  /* symbol_check_error_threshold                   dem_base:98 */
+    int32_t match_threshold;  /* overlap_offset - num_errors_allowed            dem_base:99 */
+    int32_t num_symbols;      /* rows of the look-up table (= number of masks) */
+    int32_t lut_k;            /* successors per row of symbol_lut, 0 with bit_lut */
+    int32_t reserved;
+} pcs_stitch_config;
+int pcs_stitch_create(const pcs_stitch_config* cfg, const uint8_t* bit_lut, const int32_t* symbol_lut, pcs_stitcher** out);
+int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre, const float* mag, int32_t n_sym,
+                     const int64_t* clipped, int32_t n_clipped, double sp_sym, uint8_t* bits_out, uint8_t* centres_out,
+                     uint8_t* trust_out, int32_t* n_out);
+int pcs_stitch_reset(pcs_stitcher* s);
+int pcs_stitch_destroy(pcs_stitcher* s);
+
 const char* pcs_last_error(void);
 int pcs_abi_version(void);
 

@@ -40,6 +40,11 @@ class Result(C.Structure):
         ("noise_start", C.c_int32), ("noise_len", C.c_int32), ("demod_shift", C.c_int32), ("xchg_timeout", C.c_int32)]
 
 
+class StitchConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nfft", "overlap", "overlap_offset", "error_threshold", "match_threshold",
+                                         "num_symbols", "lut_k", "reserved")]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "path", "log2_block", "valid_per_block", "num_blocks", "support_pos", "support_neg", "groups_per_cta",
@@ -76,6 +81,10 @@ SYMBOLS = {
     "pcs_peer_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "pcs_enqueue_search_push": (C.c_int, [_P, C.c_int64, C.c_int32]),
     "pcs_enqueue_owner_tail": (C.c_int, [_P, C.c_int64]),
+    "pcs_stitch_create": (C.c_int, [C.POINTER(StitchConfig), _P, _P, C.POINTER(_P)]),
+    "pcs_stitch_chunk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P, C.POINTER(C.c_int32)]),
+    "pcs_stitch_reset": (C.c_int, [_P]),
+    "pcs_stitch_destroy": (C.c_int, [_P]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -117,6 +126,62 @@ def measure_fp32_peak(device=0):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_P)
+
+
+class Stitcher:
+    """Host-side bit post-processing of a chunk (``pcs_stitch_*``): bit extraction, chunk stitching, clipped-peak
+    tagging and the uint8 casts in one native call; keeps the cross-chunk state."""
+
+    def __init__(self, *, nfft, overlap, overlap_offset, error_threshold, match_threshold, bit_lut, symbol_lut):
+        self.lib = load()
+        if bit_lut is not None:
+            self._bit = np.ascontiguousarray(np.asarray(bit_lut), dtype=np.uint8)
+            self._sym, M, K = None, len(self._bit), 0
+        else:
+            lut = np.asarray(symbol_lut)
+            if lut.ndim != 3 or lut.shape[1] != 2:
+                raise NotImplementedError("extractBitsOld is not defined by the reference either (dem_base:1017)")
+            self._sym = np.ascontiguousarray(lut, dtype=np.int32)
+            self._bit, M, K = None, lut.shape[0], lut.shape[2]
+        cfg = StitchConfig(int(nfft), int(overlap), int(overlap_offset), int(error_threshold), int(match_threshold), M, K, 0)
+        self._h = _P()
+        rc = self.lib.pcs_stitch_create(C.byref(cfg), _ptr(self._bit), _ptr(self._sym), C.byref(self._h))
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+        self._cap = 0
+
+    def __call__(self, sym, centre, mag, clipped, sp_sym):
+        n = len(sym)
+        if n > self._cap:
+            self._cap = n
+            self._bits, self._cen, self._tr = (np.empty(n, dtype=np.uint8) for _ in range(3))
+        sym = np.ascontiguousarray(sym, dtype=np.int32)
+        centre = np.ascontiguousarray(centre, dtype=np.int32)
+        mag = np.ascontiguousarray(mag, dtype=np.float32)
+        clipped = np.ascontiguousarray(clipped, dtype=np.int64)
+        n_out = C.c_int32(0)
+        rc = self.lib.pcs_stitch_chunk(self._h, _ptr(sym), _ptr(centre), _ptr(mag), n, _ptr(clipped), len(clipped),
+                                       float(sp_sym), _ptr(self._bits), _ptr(self._cen), _ptr(self._tr), C.byref(n_out))
+        if rc == -4:
+            raise IndexError(self.lib.pcs_last_error().decode())       # what the reference's np.where(...)[0][0] raises
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+        k = n_out.value
+        return self._bits[:k].copy(), self._cen[:k].copy(), self._tr[:k].copy()
+
+    def reset(self):
+        self.lib.pcs_stitch_reset(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pcs_stitch_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:

@@ -28,6 +28,8 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+int pcs_fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }   // for the other translation units
+
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
         cudaError_t e__ = (expr);                                                              \
@@ -968,7 +970,7 @@ int pcs_enqueue_device(pcs_handle* h, const void* d_chunk) {
 
 int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag) {
     if (!h) return fail(PCS_ERR_INVALID, "null handle");
-    if (!h->demodulated) return fail(PCS_ERR_STATE, "pcs_fetch before a chunk was enqueued");
+    if (!h->demodulated && !h->fetch_in_flight) return fail(PCS_ERR_STATE, "pcs_fetch before a chunk was enqueued");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (!h->fetch_in_flight) {
         if (int rc = enqueue_fetch_search(h)) return rc;

@@ -1,0 +1,203 @@
+// Host-side bit post-processing of one chunk in C++: what the reference does in NumPy after the
+// three D2H copies of cudaFindCentres -- extractBits / extractBitsNRZs (dem_base:1012-1051), checkSymbolOverlap
+// (dem_base:863-988), clipped-peak tagging of the trust (dem_base:817-837) and the uint8 output casts (dem_base:859).
+// No device code; it lives in the same shared library so the Python mirror makes one call per chunk.
+// Python slice semantics (negative starts, clamping, empty results) are reproduced exactly because the reference's
+// stitching relies on them at the chunk edges.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pycusdr_b200.h"
+
+int pcs_fail_msg(int code, const char* msg);   // pcs_api.cu
+
+namespace {
+
+struct Span {
+    long lo, hi;   // [lo, hi), already clamped to the array
+    long len() const { return hi > lo ? hi - lo : 0; }
+};
+const long NONE = INT64_MIN;
+
+// a[start:stop] on an array of n elements, Python rules (step 1)
+Span pyslice(long n, long start, long stop) {
+    long lo = start == NONE ? 0 : (start < 0 ? start + n : start);
+    long hi = stop == NONE ? n : (stop < 0 ? stop + n : stop);
+    if (lo < 0) lo = 0;
+    if (lo > n) lo = n;
+    if (hi < 0) hi = 0;
+    if (hi > n) hi = n;
+    if (hi < lo) hi = lo;
+    return {lo, hi};
+}
+
+// number of equal elements of a[sa] and b[sb], or -1 when the shapes differ (NumPy: comparison is "False")
+long matches(const uint8_t* a, Span sa, const uint8_t* b, Span sb) {
+    if (sa.len() != sb.len()) return -1;
+    long c = 0;
+    for (long i = 0; i < sa.len(); ++i) c += a[sa.lo + i] == b[sb.lo + i];
+    return c;
+}
+
+}  // namespace
+
+struct pcs_stitcher {
+    pcs_stitch_config cfg;
+    std::vector<uint8_t> bit_lut;       // [M]
+    std::vector<int32_t> symbol_lut;    // [M][2][K]
+    std::vector<uint8_t> poswinP, posSymEnd, bits, near;
+    bool have_prev = false;
+};
+
+extern "C" {
+
+int pcs_stitch_create(const pcs_stitch_config* cfg, const uint8_t* bit_lut, const int32_t* symbol_lut, pcs_stitcher** out) {
+    if (!cfg || !out) return pcs_fail_msg(PCS_ERR_INVALID, "null argument");
+    if (cfg->num_symbols < 1 || cfg->nfft < 1) return pcs_fail_msg(PCS_ERR_INVALID, "bad stitcher geometry");
+    if (!bit_lut && !(symbol_lut && cfg->lut_k > 0))
+        return pcs_fail_msg(PCS_ERR_INVALID, "neither a bit LUT nor a 3-D symbol LUT: extractBitsOld is not defined by the "
+                                             "reference either (dem_base:1017)");
+    pcs_stitcher* s = new pcs_stitcher();
+    s->cfg = *cfg;
+    if (bit_lut) s->bit_lut.assign(bit_lut, bit_lut + cfg->num_symbols);
+    else s->symbol_lut.assign(symbol_lut, symbol_lut + (size_t)cfg->num_symbols * 2 * cfg->lut_k);
+    *out = s;
+    return PCS_OK;
+}
+
+int pcs_stitch_reset(pcs_stitcher* s) {
+    if (!s) return pcs_fail_msg(PCS_ERR_INVALID, "null stitcher");
+    s->poswinP.clear();
+    s->posSymEnd.clear();
+    s->have_prev = false;
+    return PCS_OK;
+}
+
+int pcs_stitch_destroy(pcs_stitcher* s) {
+    delete s;
+    return PCS_OK;
+}
+
+int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre, const float* mag, int32_t n_sym,
+                     const int64_t* clipped, int32_t n_clipped, double sp_sym, uint8_t* bits_out, uint8_t* centres_out,
+                     uint8_t* trust_out, int32_t* n_out) {
+    if (!s || !sym || !centre || !mag || !bits_out || !centres_out || !trust_out || !n_out)
+        return pcs_fail_msg(PCS_ERR_INVALID, "null argument");
+    if (n_sym < 1) return pcs_fail_msg(PCS_ERR_INVALID, "no symbols");
+    const pcs_stitch_config& c = s->cfg;
+    const int M = c.num_symbols;
+    // trust = the first n_sym raw bytes of the float magnitudes (dem_base:472,1005-1007)
+    const uint8_t* trust = reinterpret_cast<const uint8_t*>(mag);
+    // ---- extractBits / extractBitsNRZs ----
+    std::vector<uint8_t>& bits = s->bits;
+    long n_bits, n_err = 0;
+    auto wrap = [M](int v) { return v < 0 ? v + M : v; };
+    for (int i = 0; i < n_sym; ++i)
+        if (sym[i] < -M || sym[i] >= M) return pcs_fail_msg(PCS_ERR_INVALID, "symbol index outside the look-up table");
+    if (!s->bit_lut.empty()) {
+        n_bits = n_sym;
+        bits.resize(n_bits);
+        for (long i = 0; i < n_bits; ++i) bits[i] = s->bit_lut[wrap(sym[i])];           // dem_base:1020
+    } else {
+        const int K = c.lut_k;
+        n_bits = n_sym - 1;
+        bits.resize(n_bits);
+        for (long i = 0; i < n_bits; ++i) {                                             // dem_base:1041-1051
+            const int32_t* row = &s->symbol_lut[(size_t)wrap(sym[i]) * 2 * K];
+            bool one = false, zero = false;
+            for (int k = 0; k < K; ++k) {
+                one |= row[k] == sym[i + 1];
+                zero |= row[K + k] == sym[i + 1];
+            }
+            if (!(one || zero)) { ++n_err; one = false; }                               // SYMBOL_MISMATCHVAL = 0
+            bits[i] = one;
+        }
+    }
+    // ---- checkSymbolOverlap ----
+    const int half = c.overlap / 2;                                                     // sigOverlapWin, dem_base:91
+    long start = -1, end = -1;
+    for (long i = 0; i < n_sym; ++i)
+        if (centre[i] >= half) { start = i; break; }
+    for (long i = 0; i < n_sym; ++i)
+        if (centre[i] > c.nfft - half) { end = i; break; }
+    if (start < 0 || end < 0)
+        return pcs_fail_msg(PCS_ERR_STATE, "no symbol centre inside the overlap windows (the reference raises IndexError here)");
+    const long oo = c.overlap_offset;
+    const uint8_t* b = bits.data();
+    if (n_err <= c.error_threshold && !s->poswinP.empty()) {
+        const uint8_t* P = s->poswinP.data();
+        const uint8_t* E = s->posSymEnd.data();
+        const long nP = (long)s->poswinP.size(), nE = (long)s->posSymEnd.size();
+        const Span win = pyslice(n_bits, start, end), pre = pyslice(n_bits, NONE, start);
+        auto sub = [](Span outer, long a, long z) {      // outer[a:z]
+            Span in = pyslice(outer.len(), a, z);
+            return Span{outer.lo + in.lo, outer.lo + in.hi};
+        };
+        struct Pair { const uint8_t* a; Span sa; const uint8_t* b; Span sb; };
+        const Pair pairs[6] = {
+            {P, pyslice(nP, NONE, oo), b, sub(win, NONE, oo)},                      // pre
+            {E, pyslice(nE, -oo, NONE), b, sub(pre, -oo, NONE)},                    // pos
+            {P, pyslice(nP, NONE, oo), b, sub(win, 1, oo + 1)},                     // earlyPre
+            {E, pyslice(nE, -oo - 1, -1), b, sub(pre, -oo, NONE)},                  // earlyPos
+            {P, pyslice(nP, 1, oo + 1), b, sub(win, 0, oo)},                        // latePre
+            {E, pyslice(nE, -oo, NONE), b, sub(pre, -oo - 1, -1)},                  // latePos
+        };
+        long n[6];
+        for (int k = 0; k < 6; ++k) n[k] = matches(pairs[k].a, pairs[k].sa, pairs[k].b, pairs[k].sb);
+        auto full = [&](int k) { return n[k] >= 0 && n[k] == pairs[k].sa.len(); };
+        if (!(full(0) || full(1))) {
+            long cnt[6];
+            for (int k = 0; k < 6; ++k) cnt[k] = n[k] < 0 ? 0 : n[k];
+            const long maxPre = std::max(cnt[0], std::max(cnt[2], cnt[4]));
+            const long maxPos = std::max(cnt[1], std::max(cnt[3], cnt[5]));
+            const long thr = c.match_threshold;
+            if (thr < cnt[2] && cnt[2] == maxPre) {
+                if (thr < cnt[3] && cnt[3] == maxPos) start += 1;                       // drop the first bit
+            } else if (thr < cnt[4] && cnt[4] == maxPre) {
+                if (thr < cnt[5] && cnt[5] == maxPos) start -= 1;                       // re-insert the last pre-window bit
+            }
+        }
+    }
+    const Span w = pyslice(n_bits, start, end);           // dataBits[start:end]
+    const Span wc = pyslice(n_sym, start, end);           // centres / trust [start:end]
+    const long n_win = w.len();
+    // carry for the next chunk (dem_base:977-979)
+    {
+        const Span tail = pyslice(n_bits, end, NONE);
+        s->poswinP.assign(b + tail.lo, b + tail.hi);
+        const Span last = pyslice(n_win, -oo - 1, NONE);
+        s->posSymEnd.assign(b + w.lo + last.lo, b + w.lo + last.hi);
+    }
+    // ---- outputs + clipped-peak tagging ----
+    // the three arrays have the same length except in the NRZ-S path at the very end of the chunk; the reference then
+    // fails on the boolean index -- here the shorter length is used
+    const long n_ret = std::min(n_win, wc.len());
+    for (long i = 0; i < n_ret; ++i) {
+        bits_out[i] = b[w.lo + i];
+        centres_out[i] = (uint8_t)centre[wc.lo + i];
+        trust_out[i] = trust[wc.lo + i];
+    }
+    if (n_clipped > 0) {
+        const long N = c.nfft;
+        const long span = 2 * (long)ceil(sp_sym);
+        s->near.assign((size_t)N, 0);
+        for (int k = 0; k < n_clipped; ++k) {
+            const Span r = pyslice(N, (long)clipped[k] - span, (long)clipped[k] + span + 1);
+            if (r.len() > 0) memset(s->near.data() + r.lo, 1, (size_t)r.len());
+        }
+        for (long i = 0; i < n_ret; ++i) {
+            long ci = centre[wc.lo + i];
+            if (ci < 0) ci += N;
+            if (ci < 0 || ci >= N) return pcs_fail_msg(PCS_ERR_STATE, "symbol centre outside the chunk while tagging clipped peaks");
+            if (s->near[ci]) trust_out[i] = (uint8_t)(int8_t)-2;
+        }
+    }
+    *n_out = (int32_t)n_ret;
+    return PCS_OK;
+}
+
+}  // extern "C"

@@ -35,7 +35,8 @@ SNR_WINDOW = 5              # dem_base:620
 
 class Demodulator:
 
-    def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True):
+    def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True,
+                 native_post=True):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
@@ -124,6 +125,14 @@ class Demodulator:
             code_search_mask_offset=self.CODE_SEARCH_MASK_OFFSET, samples_per_sym=self.spsym, path=path,
             log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph)
         self.GPU_bufSignalTime_cpu_handle = self._engine.host_buffer
+        # bit extraction + chunk stitching + trust tagging in one native call (the NumPy methods below stay as the
+        # readable mirror of dem_base:863-1051 and are what ``native_post=False`` runs)
+        self._stitch = None
+        if native_post and (self.bitLUT is not None or len(np.shape(self.symbolLUT)) == 3):
+            self._stitch = _native.Stitcher(
+                nfft=self.Nfft, overlap=self.sigOverlap, overlap_offset=self.overlapOffset,
+                error_threshold=self.symbol_check_error_threshold, match_threshold=self.symbol_check_match_threshold,
+                bit_lut=self.bitLUT, symbol_lut=self.symbolLUT)
 
         # cross-call state
         self.clippedPeakIPure = []
@@ -276,6 +285,9 @@ class Demodulator:
         trustSymbol = np.ascontiguousarray(magnitudes, dtype=np.float32).view(TRUSTTYPE)[:len(idxSymbol)].copy()
         self.last.update(shift=int(res.demod_shift), timing=np.array(res.timing[:], dtype=np.float32), spSym=spSym,
                          codeOffset=np.float64(res.code_offset), sym=idxSymbol, centres=centres, mag=magnitudes)
+        if self._stitch is not None:
+            bitsU8, centresU8, trustU8 = self._stitch(idxSymbol, centres, magnitudes, self.clippedPeakIPure, spSym)
+            return bitsU8, centresU8, trustU8, spSym
         dataBits, symError = self.extractBits(centres, idxSymbol)
         centresWin, dataBitsWin, trustSymbolWin, _ = self.checkSymbolOverlap(
             len(symError), centres, idxSymbol, dataBits, trustSymbol)

@@ -1,0 +1,78 @@
+"""The native (C++) bit post-processing against the oracle's host functions -- which are themselves pinned to the
+reference's own Python (tests/test_oracle_golden.py).  Runs on the CPU: the stitcher has no device code."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from pycusdr_b200 import _native
+from pycusdr_b200.protocol.benchmark.bench_protocols import _nrzs_lut
+
+N, OVL, OO, ERR_THR, MATCH_THR = 8192, 1024, 20, 1000, 10
+
+
+def _oracle_chunk(state, sym, centres, mag, clipped, spSym, bitLUT, symbolLUT):
+    trust = O.trust_from_magnitudes(mag, len(sym))
+    bits, err = O.extract_bits(sym, bitLUT, symbolLUT)
+    cW, bW, tW = O.check_symbol_overlap(state, len(err), centres, bits, trust, N, OVL // 2, OO, ERR_THR, MATCH_THR)
+    tW = O.tag_clipped_peaks(tW, cW, clipped, spSym, N)
+    return bW.astype(np.uint8), cW.astype(np.uint8), tW.astype(np.uint8)
+
+
+def _stream(rng, n_chunks, M, sps, slip_at=(), noisy_at=()):
+    """Symbol decisions of consecutive overlapping chunks of one long random symbol sequence."""
+    total = rng.randint(0, M, size=n_chunks * (N // sps) + 64).astype(np.int32)
+    step_syms = (N - OVL) // sps
+    out = []
+    for c in range(n_chunks):
+        off = rng.uniform(0, sps)
+        S = int(N / sps)
+        k0 = c * step_syms + (1 if c in slip_at else 0) - (1 if (c + 100) in slip_at else 0)
+        sym = total[k0:k0 + S].copy()
+        if c in noisy_at:
+            flip = rng.rand(S) < 0.3
+            sym[flip] = rng.randint(0, M, size=int(flip.sum()))
+        if c == 2:
+            sym[5] = -1                                         # all-zero window (kern:104-105 initial values)
+        centres = (np.arange(S) * sps + off + rng.randint(-2, 3, size=S)).astype(np.int32)
+        mag = (rng.rand(S) * 10 ** rng.uniform(-3, 3)).astype(np.float32)
+        out.append((sym, centres, mag))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["bitlut", "nrzs"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_native_stitcher_matches_oracle(kind, seed):
+    rng = np.random.RandomState(seed)
+    if kind == "bitlut":
+        M, bitLUT, symbolLUT = 8, np.array([0, 0, 1, 1, 0, 0, 1, 1]), []
+    else:
+        M, bitLUT, symbolLUT = 16, None, _nrzs_lut(5)
+    st = _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
+                          bit_lut=bitLUT, symbol_lut=symbolLUT)
+    state = O.OverlapState()
+    chunks = _stream(rng, 14, M, 16, slip_at=(3, 7, 108, 111), noisy_at=(5, 9))
+    adjusted = 0
+    for c, (sym, centres, mag) in enumerate(chunks):
+        clipped = np.sort(rng.choice(N, size=rng.randint(0, 4), replace=False)) if c % 3 == 1 else np.array([], dtype=np.int64)
+        if c == 4:
+            clipped = np.array([3, 10, N - 2])                 # slices that start below zero / end past the chunk
+        spSym = 16.0 + rng.uniform(-0.4, 0.4)
+        want = _oracle_chunk(state, sym, centres, mag, clipped, spSym, bitLUT, symbolLUT)
+        got = st(sym, centres, mag, clipped, spSym)
+        for g, w, name in zip(got, want, ("bits", "centres", "trust")):
+            np.testing.assert_array_equal(g, w, err_msg=f"chunk {c}: {name}")
+        adjusted += int(len(want[0]) != np.sum((centres >= OVL // 2) & (np.arange(len(centres)) < np.argmax(centres > N - OVL // 2))))
+    assert adjusted >= 1, "the +-1 symbol realignment branch was never taken: the test stream is too tame"
+
+
+def test_native_stitcher_errors_mirror_the_reference():
+    st = _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
+                          bit_lut=np.array([0, 1]), symbol_lut=[])
+    sym = np.zeros(16, np.int32)
+    with pytest.raises(IndexError):                            # no centre beyond Nfft - overlap/2
+        st(sym, np.arange(16, dtype=np.int32) * 16, np.ones(16, np.float32), [], 16.0)
+    with pytest.raises(_native.NativeError):                   # symbol outside the table
+        st(sym + 5, np.arange(16, dtype=np.int32) * 300, np.ones(16, np.float32), [], 16.0)
+    with pytest.raises(NotImplementedError):
+        _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
+                         bit_lut=None, symbol_lut=np.zeros((4, 3)))
