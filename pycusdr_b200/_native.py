@@ -94,6 +94,7 @@ SYMBOLS = {
 }
 
 _lib = None
+_live = None      # weak set of Engine / Stitcher objects, closed at interpreter exit while CUDA is still up
 
 
 def load():
@@ -111,6 +112,18 @@ def load():
         if lib.pcs_abi_version() != ABI_VERSION:
             raise ImportError(f"ABI mismatch: library {lib.pcs_abi_version()}, binding {ABI_VERSION}")
         _lib = lib
+        import atexit
+        import weakref
+        global _live
+        _live = weakref.WeakSet()
+
+        def _close_all():
+            for obj in list(_live):
+                try:
+                    obj.close()
+                except Exception:
+                    pass
+        atexit.register(_close_all)
     return _lib
 
 
@@ -173,9 +186,10 @@ class Stitcher:
         self.lib.pcs_stitch_reset(self._h)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self.lib.pcs_stitch_destroy(self._h)
-            self._h = _P()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = None
+            self.lib.pcs_stitch_destroy(h)
 
     def __del__(self):
         try:
@@ -202,6 +216,7 @@ class Engine:
         self._h = _P()
         self.nfft, self.D, self.M = nfft, num_dopplers + element_offset, masks.shape[0]
         self._check(self.lib.pcs_create(C.byref(cfg), _ptr(shifts), _ptr(masks), C.byref(self._h)))
+        _live.add(self)
         self.max_sym = self.lib.pcs_max_symbols(self._h)
         buf = (C.c_float * (2 * nfft)).from_address(self.lib.pcs_host_buffer(self._h))
         self.host_buffer = np.frombuffer(buf, dtype=np.complex64)
@@ -215,10 +230,11 @@ class Engine:
             raise NativeError(rc, self.lib.pcs_last_error().decode())
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
             self.host_buffer = None
-            self.lib.pcs_destroy(self._h)
-            self._h = _P()
+            self._h = None
+            self.lib.pcs_destroy(h)
 
     def __del__(self):
         try:

@@ -100,7 +100,8 @@ struct pcs_handle {
     size_t xchg_bytes = 0;
     unsigned char* peer_base[16] = {};
     int peer_rank = 0, peer_world = 0;
-    bool peers_attached = false;
+    bool peers_attached = false, tail_on_side = false;
+    cudaEvent_t ev_push = nullptr;
     float *tab_E = nullptr, *tab_pv = nullptr;   // tables the search stage writes / the estimate stage reads
     int* tab_po = nullptr;
     cudaStream_t side = nullptr;       // forked branch of the graph: chunk spectrum -> SNR bins (off the critical path)
@@ -426,6 +427,7 @@ int pcs_destroy(pcs_handle* h) {
     if (!h) return PCS_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->side) cudaStreamSynchronize(h->side);
     for (void* p : h->dev_allocs) cudaFree(p);
     void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre};
     for (void* p : pinned)
@@ -435,7 +437,7 @@ int pcs_destroy(pcs_handle* h) {
     if (h->d_xchg) cudaFree(h->d_xchg);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->side) cudaStreamDestroy(h->side);
-    for (cudaEvent_t e : {h->ev_fork, h->ev_est, h->ev_side})
+    for (cudaEvent_t e : {h->ev_fork, h->ev_est, h->ev_side, h->ev_push})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -472,6 +474,7 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_est, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming));
     h->N = N;
     h->logN = ilog2(N);
     h->logN1 = h->logN / 2;
@@ -976,7 +979,12 @@ int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_
         if (int rc = enqueue_fetch_search(h)) return rc;
         if (int rc = enqueue_fetch_demod(h)) return rc;
     }
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->tail_on_side) {
+        CUDA_TRY(cudaStreamSynchronize(h->side));
+        h->tail_on_side = false;
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     h->fetch_in_flight = false;
     h->h_res->demod_shift = h->h_res->shift;
     copy_search_out(h, res, E_out);
@@ -1225,21 +1233,35 @@ int pcs_enqueue_owner_tail(pcs_handle* h, int64_t seq) {
     if (!h->uploaded) return fail(PCS_ERR_STATE, "tail before upload");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int parity = (int)((seq / h->peer_world) & 1);
-    peer_wait_kernel<<<1, 32, 0, h->stream>>>(xchg_flags(h, h->d_xchg, parity), h->peer_world, (unsigned long long)seq + 1ull,
-                                              h->d_res);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    h->tab_E = xchg_table(h, h->d_xchg, parity, 0);
-    h->tab_pv = xchg_table(h, h->d_xchg, parity, 1);
-    h->tab_po = reinterpret_cast<int*>(xchg_table(h, h->d_xchg, parity, 2));
-    int rc = enqueue_estimate(h);
-    h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
+    // The tail runs on the handle's second stream so that this rank's next searches do not queue behind it (it mostly
+    // waits for the slowest peer and then runs latency-bound kernels on a few SMs).  It is ordered after this rank's own
+    // push by an event, so the wait kernel below only ever waits for flags written from OTHER GPUs.
+    cudaStream_t main_s = h->stream;
+    if (!h->profiling) {
+        CUDA_TRY(cudaEventRecord(h->ev_push, main_s));
+        CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_push, 0));
+        h->stream = h->side;
+    }
+    int rc = 0;
+    do {
+        peer_wait_kernel<<<1, 32, 0, h->stream>>>(xchg_flags(h, h->d_xchg, parity), h->peer_world,
+                                                  (unsigned long long)seq + 1ull, h->d_res);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(PCS_ERR_CUDA, "peer_wait_kernel launch failed"); break; }
+        h->tab_E = xchg_table(h, h->d_xchg, parity, 0);
+        h->tab_pv = xchg_table(h, h->d_xchg, parity, 1);
+        h->tab_po = reinterpret_cast<int*>(xchg_table(h, h->d_xchg, parity, 2));
+        rc = enqueue_estimate(h);
+        h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
+        if (rc) break;
+        if ((rc = enqueue_demod(h, -1, false))) break;
+        if ((rc = enqueue_fetch_search(h))) break;
+        if ((rc = enqueue_fetch_demod(h))) break;
+    } while (0);
+    h->tail_on_side = (h->stream == h->side);
+    h->stream = main_s;
     if (rc) return rc;
-    h->searched = true;
-    if ((rc = enqueue_demod(h, -1, false))) return rc;
-    h->demodulated = true;
-    if ((rc = enqueue_fetch_search(h))) return rc;
-    if ((rc = enqueue_fetch_demod(h))) return rc;
+    h->searched = h->demodulated = true;
     h->fetch_in_flight = true;
     return PCS_OK;
 }
