@@ -536,6 +536,14 @@ def main():
         "chunk_frac": max(F_alg / (fp32_peak * 1e12), B_alg / (hbm_peak * 1e9)) * 1e3 / ms_step if world == 1 else None,
         "traffic": None,
     }
+    try:        # DRAM bytes of one launch of this kernel from the committed ncu --set full capture (same workload, 1 GPU)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get(roof["kernel"])
+        if t and t["workload"] == args.workload and world == 1:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = f"ncu --set full, capture {t['capture']} (profiles/)"
+    except (OSError, ValueError, KeyError):
+        pass
     stages = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
 
     cpu = None
