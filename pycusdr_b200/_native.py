@@ -138,7 +138,8 @@ def measure_fp32_peak(device=0):
 
 
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(_P)
+    """NULL or the address of a NumPy array's buffer (``a.ctypes.data_as`` costs ~3 us a call; this does not)."""
+    return None if a is None else a.__array_interface__["data"][0]
 
 
 class Stitcher:

@@ -274,8 +274,11 @@ PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, 
 
 __global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
     __shared__ float2 sbuf[16][272];
+    extern __shared__ float s_acc[];          // [16 groups][2][M][17]: per-lane sum / max of every mask
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
+    float* acc_sum = s_acc + (size_t)g * 2 * p.M * 17;
+    float* acc_max = acc_sum + (size_t)p.M * 17;
     float2 tw[16];
 #pragma unroll
     for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
     float2 xb[16];
     os256_block_spectrum(p, it, buf, tw, t, xb);
     const unsigned vm = os256_valid_mask(p, it, t);
-    float ks0 = 0.f, ks1 = 0.f, kb0 = 0.f, kb1 = 0.f;
+#pragma unroll 1
     for (int m = 0; m < p.M; ++m) {
         float2 v[16];
         os256_filter(p, m, xb, buf, tw, t, v);
@@ -299,19 +302,24 @@ __global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
             sum += mag;
             best = fmaxf(best, mag);
         }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-        }
-        if (t == (m & 15)) {
-            if (m < 16) { ks0 = sum; kb0 = best; } else { ks1 = sum; kb1 = best; }
-        }
+        // no cross-lane traffic inside the loop: the per-lane partials are parked in shared memory
+        acc_sum[m * 17 + t] = sum;
+        acc_max[m * 17 + t] = best;
     }
-    if (live) {
-        const size_t o = ((size_t)it.blk * p.D + it.d) * p.M;
-        if (t < p.M) { p.psum[o + t] = ks0; p.pmax[o + t] = kb0; }
-        if (t + 16 < p.M) { p.psum[o + t + 16] = ks1; p.pmax[o + t + 16] = kb1; }
+    __syncwarp();
+    // lane m folds the 16 lanes of mask m in lane order (fixed order -> bit-reproducible) and stores the pair
+    for (int m = t; m < p.M; m += 16) {
+        float sum = 0.f, best = 0.f;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            sum += acc_sum[m * 17 + l];
+            best = fmaxf(best, acc_max[m * 17 + l]);
+        }
+        if (live) {
+            const size_t o = ((size_t)it.blk * p.D + it.d) * p.M + m;
+            p.psum[o] = sum;
+            p.pmax[o] = best;
+        }
     }
 }
 
@@ -328,7 +336,23 @@ __global__ void __launch_bounds__(1024) search_reduce256_kernel(const float* __r
     float sum = 0.f, best = -1.f;
     int bb = 0x7fffffff;
     if (col < DM) {
-        for (int b = z + PCS_RED_SLICES * w; b < nblk; b += PCS_RED_SLICES * 32) {
+        constexpr int STEP = PCS_RED_SLICES * 32;
+        int b = z + PCS_RED_SLICES * w;
+        for (; b + 3 * STEP < nblk; b += 4 * STEP) {        // four independent loads in flight, same summation order
+            float s4[4], v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t o = (size_t)(b + u * STEP) * DM + col;
+                s4[u] = __ldg(&psum[o]);
+                v4[u] = __ldg(&pmax[o]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sum += s4[u];
+                if (v4[u] > best) { best = v4[u]; bb = b + u * STEP; }
+            }
+        }
+        for (; b < nblk; b += STEP) {
             const size_t o = (size_t)b * DM + col;
             sum += psum[o];
             const float v = pmax[o];
@@ -359,7 +383,9 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
                                                                 const float* __restrict__ part_max,
                                                                 const int* __restrict__ part_blk,
                                                                 float* __restrict__ Efull, float* __restrict__ peak_val,
-                                                                int* __restrict__ peak_off) {
+                                                                int* __restrict__ peak_off, unsigned int* done_counter,
+                                                                unsigned long long* arrival_flag,
+                                                                unsigned long long arrival_value) {
     __shared__ float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
@@ -411,6 +437,20 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
         if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
     }
     if (live && t == 0) peak_off[col] = idx == 0x7fffffff ? 0 : idx;
+    // Bin sharding over peer memory: the three tables above may live in another GPU's exchange region.  The last CTA
+    // to finish publishes this rank's arrival there (release at system scope after every CTA's stores are fenced).
+    if (arrival_flag != nullptr) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *done_counter = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(arrival_flag), "l"(arrival_value) : "memory");
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

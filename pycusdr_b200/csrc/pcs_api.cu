@@ -101,6 +101,9 @@ struct pcs_handle {
     unsigned char* peer_base[16] = {};
     int peer_rank = 0, peer_world = 0;
     bool peers_attached = false, tail_on_side = false;
+    unsigned int* d_done = nullptr;                       // CTA completion counter of the locate kernel
+    unsigned long long* push_flag = nullptr;              // when set, the search stage publishes its arrival there
+    unsigned long long push_value = 0;
     cudaEvent_t ev_push = nullptr;
     float *tab_E = nullptr, *tab_pv = nullptr;   // tables the search stage writes / the estimate stage reads
     int* tab_po = nullptr;
@@ -413,6 +416,8 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_part_sum, (size_t)PCS_RED_SLICES * D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_part_max, (size_t)PCS_RED_SLICES * D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_part_blk, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_done, (size_t)1)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
     h->fast256 = true;
     return 0;
 }
@@ -631,8 +636,14 @@ static int enqueue_search_local256(pcs_handle* h) {
         StageTimer t(h, PCS_STAGE_SEARCH);
         const long long items = (long long)p.nblk * Dl;
         h->search_ctas = (int)((items + 15) / 16);
-        h->search_smem = (int)(16 * 272 * sizeof(float2));
-        search_os256_kernel<<<h->search_ctas, 256, 0, h->stream>>>(p);
+        const size_t acc_bytes = (size_t)16 * 2 * p.M * 17 * sizeof(float);
+        h->search_smem = (int)(16 * 272 * sizeof(float2) + acc_bytes);
+        static size_t configured = 0;          // static + dynamic shared memory exceeds the 48 KB default
+        if (configured < acc_bytes) {
+            CUDA_TRY(cudaFuncSetAttribute(search_os256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+            configured = acc_bytes;
+        }
+        search_os256_kernel<<<h->search_ctas, 256, acc_bytes, h->stream>>>(p);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -642,7 +653,9 @@ static int enqueue_search_local256(pcs_handle* h) {
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_part_sum, h->d_part_max, h->d_part_blk,
-                                                                  h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0);
+                                                                  h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0,
+                                                                  h->d_done, h->push_flag, h->push_value);
+    h->push_flag = nullptr;       // consumed: the locate kernel raises the flag itself
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1217,13 +1230,19 @@ int pcs_enqueue_search_push(pcs_handle* h, int64_t seq, int32_t owner) {
     h->tab_E = xchg_table(h, base, parity, 0);
     h->tab_pv = xchg_table(h, base, parity, 1);
     h->tab_po = reinterpret_cast<int*>(xchg_table(h, base, parity, 2));
+    // ... and then raises its arrival flag there: from the last CTA of the locate kernel (256-point path) or from a
+    // one-thread kernel after the reduction (generic path), with a system-scope release
+    h->push_flag = xchg_flags(h, base, parity) + h->peer_rank;
+    h->push_value = (unsigned long long)seq + 1ull;
     const int rc = enqueue_search_local(h);
     h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
-    if (rc) return rc;
-    // ... and then raises its arrival flag there (system-scope release after the kernel boundary)
-    peer_flag_kernel<<<1, 1, 0, h->stream>>>(xchg_flags(h, base, parity) + h->peer_rank, (unsigned long long)seq + 1ull);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
+    if (rc) { h->push_flag = nullptr; return rc; }
+    if (h->push_flag) {
+        peer_flag_kernel<<<1, 1, 0, h->stream>>>(h->push_flag, h->push_value);
+        h->push_flag = nullptr;
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     return PCS_OK;
 }
 

@@ -215,6 +215,15 @@ class Demodulator:
         wins = None
         if res is not None and res.sig_len > 0 and windowWidth == SNR_WINDOW:
             sig, noise = self._engine.snr_windows(res)
+            # common case: neither window touches the ends of the spectrum, so the reference's slices
+            # X[a-w : b+w] are exactly the two windows the device gathered (dem_base:657-661)
+            w = windowWidth
+            if (lo <= hi and nlo <= nhi and lo - w >= 0 and nlo - w >= 0 and hi + w <= N and nhi + w <= N
+                    and res.sig_start == lo - w and res.noise_start == nlo - w
+                    and len(sig) == hi - lo + 2 * w and len(noise) == nhi - nlo + 2 * w):
+                with np.errstate(all="ignore"):
+                    ratio = np.float32(np.mean(np.abs(sig))) / np.float32(np.mean(np.abs(noise)))
+                    return np.float64(20) * np.log10(np.float64(ratio) - 1)
             wins = ((res.sig_start, sig), (res.noise_start, noise))
         full = [None]
 
