@@ -365,6 +365,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--log2-block", type=int, default=0)
+    ap.add_argument("--groups-per-cta", type=int, default=0, help="tuning knob of the 256-point search kernel")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=2,
@@ -407,7 +408,7 @@ def main():
     dev_chunks = torch.from_numpy(host_chunks).cuda()
     ring_bytes = dev_chunks.numel() * 8
 
-    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block)
+    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta)
     eng = dem._engine
     D, M = eng.D, eng.M
     plan = eng.plan()
@@ -461,7 +462,8 @@ def main():
         # chunks in flight: handle k % K takes chunk k, so the latency-bound tail of one chunk (estimate, demod, timing,
         # symbol decisions, result copies) overlaps the search kernel of the next one
         K = max(1, args.inflight)
-        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block) for _ in range(K - 1)]
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta)
+                 for _ in range(K - 1)]
         engs = [eng] + [d._engine for d in extra]
         streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
 

@@ -272,9 +272,10 @@ PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, 
     return vm;
 }
 
-__global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
-    __shared__ float2 sbuf[16][272];
-    extern __shared__ float s_acc[];          // [16 groups][2][M][17]: per-lane sum / max of every mask
+template <int G>     // groups (half warps) per CTA
+__global__ void __launch_bounds__(G * 16, 32 / G) search_os256_kernel(Os256Params p) {
+    __shared__ float2 sbuf[G][272];
+    extern __shared__ float s_acc[];          // [G groups][2][M][17]: per-lane sum / max of every mask
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
     float* acc_sum = s_acc + (size_t)g * 2 * p.M * 17;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) search_os256_kernel(Os256Params p) {
     for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
     tw[0] = make_float2(1.f, 0.f);
     const long long total = (long long)p.nblk * p.D;
-    long long item = (long long)blockIdx.x * 16 + g;
+    long long item = (long long)blockIdx.x * G + g;
     const bool live = item < total;
     if (!live) item = total - 1;          // keep the warp convergent; results of the duplicate are dropped
     const Os256Item it = os256_item(p, item);

@@ -635,15 +635,17 @@ static int enqueue_search_local256(pcs_handle* h) {
     {
         StageTimer t(h, PCS_STAGE_SEARCH);
         const long long items = (long long)p.nblk * Dl;
-        h->search_ctas = (int)((items + 15) / 16);
-        const size_t acc_bytes = (size_t)16 * 2 * p.M * 17 * sizeof(float);
-        h->search_smem = (int)(16 * 272 * sizeof(float2) + acc_bytes);
-        static size_t configured = 0;          // static + dynamic shared memory exceeds the 48 KB default
-        if (configured < acc_bytes) {
-            CUDA_TRY(cudaFuncSetAttribute(search_os256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-            configured = acc_bytes;
+        const int G = h->cfg.reserved[1] == 8 ? 8 : 16;      // groups per CTA (tuning knob; 16 = default)
+        h->search_ctas = (int)((items + G - 1) / G);
+        const size_t acc_bytes = (size_t)G * 2 * p.M * 17 * sizeof(float);
+        h->search_smem = (int)(G * 272 * sizeof(float2) + acc_bytes);
+        static size_t configured[2] = {0, 0};          // static + dynamic shared memory may exceed the 48 KB default
+        auto kern = G == 8 ? search_os256_kernel<8> : search_os256_kernel<16>;
+        if (configured[G == 8] < acc_bytes) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+            configured[G == 8] = acc_bytes;
         }
-        search_os256_kernel<<<h->search_ctas, 256, acc_bytes, h->stream>>>(p);
+        kern<<<h->search_ctas, G * 16, acc_bytes, h->stream>>>(p);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
