@@ -1,0 +1,169 @@
+"""Edge cases of the hot path on the GPU: smallest / largest chunk, single Doppler bin, odd mask counts, the noise
+row, narrow symbol windows, all-zero input, NaN estimate, bad filter banks, call-order errors."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import signals as S
+from pycusdr_b200 import _native
+from tests.helpers import RADIO, conf_variant, protocol_for, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Proto:
+    """Wraps a protocol and overrides its filter bank (to exercise mask counts the shipped protocols do not have)."""
+
+    def __init__(self, base, keep=None, sum_all=True, bad=None):
+        self.base, self.keep, self.bad = base, keep, bad
+        self.name = base.name
+        self.SUM_ALL_MASKS_PYTHON = sum_all
+
+    def get_filter(self, Nfft, spSym, maskSize):
+        n, masks = self.base.get_filter(Nfft, spSym, maskSize)
+        if self.keep is not None:
+            masks = np.ascontiguousarray(masks[self.keep])
+            n = len(masks)
+        if self.bad == "shape":
+            return n, masks[:, :-1]
+        if self.bad == "dtype":
+            return n, masks.astype(np.complex128)
+        return n, masks
+
+    def get_symbolLUT2(self, maskSize):
+        lut, sl = self.base.get_symbolLUT2(maskSize)
+        if self.keep is not None and lut is not None:
+            lut = np.asarray(lut)[self.keep]
+        return lut, sl
+
+
+def _pair(conf, P, **kw):
+    from pycusdr_b200.demodulator import UHF
+    return UHF.Demodulator(conf, P, RADIO, **kw), O.OracleDemodulator(conf, P, RADIO)
+
+
+def _chunk(N, seed, amp=0.3):
+    sig, _ = S.get_padded_packet("GMSK", 16, 153600, pad=64)
+    rng = np.random.RandomState(seed)
+    x = amp * (rng.randn(N) + 1j * rng.randn(N))
+    n = min(N - 128, len(sig))
+    x[64:64 + n] += sig[:n]
+    return x.astype(np.complex64)
+
+
+def _compare(dem, orc, x, exact_bits=True):
+    for d in (dem, orc):
+        d.get_signalBufferHostPointer()[:] = x
+    fa = dem.uploadAndFindCarrier(dem.get_signalBufferHostPointer())
+    fb = orc.uploadAndFindCarrier(orc.get_signalBufferHostPointer())
+    ba, bb = dem.demodulate(), orc.demodulate()
+    assert rel_err(dem.last["E"], orc.last["E"]) < 1e-4
+    assert dem.last["shift"] == orc.last["shift"]
+    assert dem.last["timing"][0] == orc.last["timing"][0]
+    assert fa[0] == pytest.approx(fb[0], abs=1e-2)
+    assert len(dem.last["sym"]) == len(orc.last["sym"])
+    same = np.mean(dem.last["sym"] == orc.last["sym"])
+    assert same > 0.995
+    if exact_bits and same == 1.0:
+        np.testing.assert_array_equal(ba[0], bb[0])
+        np.testing.assert_array_equal(ba[2], bb[2])       # trust bytes
+    return fa, fb
+
+
+@pytest.mark.parametrize("blockSize,bins", [(12, 3), (13, 1), (20, 2)])
+def test_chunk_size_extremes(blockSize, bins):
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=blockSize, doppCarrierSteps=bins)
+    dem, orc = _pair(conf, protocol_for(conf))
+    _compare(dem, orc, _chunk(2 ** blockSize, blockSize))
+
+
+@pytest.mark.parametrize("keep,sum_all", [([0], True), ([1, 2, 5], False), ([0, 1, 2, 3, 4, 6], True), (list(range(8)), False)])
+def test_mask_counts_and_sum_modes(keep, sum_all):
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=13, doppCarrierSteps=16)
+    P = _Proto(protocol_for(conf), keep=keep, sum_all=sum_all)
+    dem, orc = _pair(conf, P)
+    assert dem.num_masks == len(keep)
+    _compare(dem, orc, _chunk(2 ** 13, len(keep)), exact_bits=False)
+
+
+def test_thirty_two_masks_nrzs_protocol_and_noise_row():
+    conf = conf_variant("benchmark/bench_BPSK.json", blockSize=14, doppCarrierSteps=12, noise_measure_offset_Hz=55000.0)
+    dem, orc = _pair(conf, protocol_for(conf))
+    assert dem.doppIdxArrayOffset == 1 and dem.doppIdxArrayLen == 13
+    sig, _ = S.get_padded_packet("BPSK", 16, 153600, pad=64)
+    rng = np.random.RandomState(3)
+    x = (sig[:2 ** 14] + 0.05 * (rng.randn(2 ** 14) + 1j * rng.randn(2 ** 14))).astype(np.complex64)
+    fa, fb = _compare(dem, orc, x, exact_bits=False)
+    assert fa[1] == pytest.approx(fb[1], rel=1e-4, abs=1e-3)      # metric uses max / E[noise row] (kern:550-554)
+
+
+@pytest.mark.parametrize("W", [1, 3, 15])
+def test_symbol_window_widths(W):
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=13, doppCarrierSteps=8)
+    conf["GPU"]["UHF"]["bitWindowWidth"] = W
+    dem, orc = _pair(conf, protocol_for(conf))
+    _compare(dem, orc, _chunk(2 ** 13, 40 + W), exact_bits=False)
+
+
+def test_all_zero_chunk_gives_the_reference_nan_branch():
+    """E == 0 everywhere -> 0/0 in findDopplerEst -> int(nan) raises in the reference, which returns zeros and keeps
+    going (dem_base:625-630); symbols of an all-zero surface are -1 (kern:104-105)."""
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=12, doppCarrierSteps=4)
+    dem, orc = _pair(conf, protocol_for(conf))
+    x = np.zeros(2 ** 12, np.complex64)
+    for d in (dem, orc):
+        d.get_signalBufferHostPointer()[:] = x
+    fa = dem.uploadAndFindCarrier(dem.get_signalBufferHostPointer())
+    fb = orc.uploadAndFindCarrier(orc.get_signalBufferHostPointer())
+    assert fa[0] == fb[0] == 0 and fa[1] == fb[1] == 0 and fa[3] == fb[3] == 0
+    assert dem.dopplerIdxlast == 0 and orc.dopplerIdxlast == 0
+    assert np.all(dem.last["E"] == 0)
+
+
+def test_bad_filter_banks_raise_like_the_reference():
+    from pycusdr_b200.demodulator import UHF
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=12, doppCarrierSteps=4)
+    base = protocol_for(conf)
+    with pytest.raises(ValueError):
+        UHF.Demodulator(conf, _Proto(base, bad="shape"), RADIO)       # dem_base:252-255
+    with pytest.raises(TypeError):
+        UHF.Demodulator(conf, _Proto(base, bad="dtype"), RADIO)       # dem_base:256-257
+
+
+def test_call_order_and_argument_errors():
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=12, doppCarrierSteps=4)
+    from pycusdr_b200.demodulator import UHF
+    dem = UHF.Demodulator(conf, protocol_for(conf), RADIO, fused=False)
+    eng = dem._engine
+    with pytest.raises(_native.NativeError) as e:
+        eng.search()
+    assert e.value.code == -4 and "before pcs_upload" in str(e.value)
+    eng.upload()
+    with pytest.raises(_native.NativeError):
+        eng.demod(-1)                                             # no search yet: nothing selected on the device
+    with pytest.raises(_native.NativeError):
+        eng.demod(2 ** 12)                                        # shift outside [0, nfft)
+    with pytest.raises(_native.NativeError):
+        eng.set_bin_range(3, 2)
+    res, E = eng.search()
+    assert res.status in (0, 1)
+    # oversized / unsupported geometry is refused at creation
+    with pytest.raises(_native.NativeError):
+        _native.Engine(device=0, nfft=1000, num_dopplers=2, element_offset=0, shifts=np.zeros(2, np.int32),
+                       masks=np.zeros((1, 1000), np.complex64), window_width=7, sum_all_masks=True,
+                       code_search_mask_offset=0, samples_per_sym=16)
+    with pytest.raises(_native.NativeError):
+        _native.Engine(device=0, nfft=4096, num_dopplers=2, element_offset=0, shifts=np.zeros(2, np.int32),
+                       masks=np.zeros((33, 4096), np.complex64), window_width=7, sum_all_masks=True,
+                       code_search_mask_offset=0, samples_per_sym=16)
+
+
+def test_caller_supplied_array_is_copied_into_the_pinned_buffer():
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=12, doppCarrierSteps=4)
+    dem, orc = _pair(conf, protocol_for(conf))
+    x = _chunk(2 ** 12, 9)
+    fa = dem.uploadAndFindCarrier(x.copy())                       # not the pinned buffer
+    orc.get_signalBufferHostPointer()[:] = x
+    fb = orc.uploadAndFindCarrier(orc.get_signalBufferHostPointer())
+    assert fa[0] == pytest.approx(fb[0], abs=1e-2)
+    assert np.array_equal(dem.get_signalBufferHostPointer(), x)
