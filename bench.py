@@ -364,8 +364,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--log2-block", type=int, default=0)
     ap.add_argument("--groups-per-cta", type=int, default=0, help="tuning knob of the 256-point search kernel")
+    ap.add_argument("--xb-smem", action="store_true", help="tuning knob: block spectrum in shared memory")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=2,
@@ -408,7 +410,7 @@ def main():
     dev_chunks = torch.from_numpy(host_chunks).cuda()
     ring_bytes = dev_chunks.numel() * 8
 
-    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta)
+    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem)
     eng = dem._engine
     D, M = eng.D, eng.M
     plan = eng.plan()
@@ -462,7 +464,7 @@ def main():
         # chunks in flight: handle k % K takes chunk k, so the latency-bound tail of one chunk (estimate, demod, timing,
         # symbol decisions, result copies) overlaps the search kernel of the next one
         K = max(1, args.inflight)
-        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta)
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem)
                  for _ in range(K - 1)]
         engs = [eng] + [d._engine for d in extra]
         streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
@@ -565,6 +567,31 @@ def main():
     prof = eng.profile()
     eng.set_profiling(False)
 
+    # ---- labelled variant: Parseval energies (no inverse transforms, no peak) on the same chunks, one in flight ----
+    variants = {}
+    if world == 1 and not args.no_variants:
+        demv = UHF.Demodulator(conf, protocol, RADIO, path=_native.PATH_PARSEVAL)
+        ev, sv = demv._engine, torch.cuda.ExternalStream(demv._engine.stream)
+        for i in range(10):
+            ev.enqueue_device(ptrs[i % ring])
+            ev.fetch()
+        torch.cuda.synchronize()
+        nv = min(args.steps, 200)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(sv)
+        ck = 0
+        for i in range(nv):
+            ev.enqueue_device(ptrs[(10 + i) % ring])
+            ck += int(ev.fetch()[0].shift)
+        b.record(sv)
+        torch.cuda.synchronize()
+        msv = a.elapsed_time(b) / nv
+        variants["parseval"] = {
+            "value": step_samples / (msv * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": msv, "chunks_in_flight": 1,
+            "note": "LABELLED ALTERNATIVE, not the headline: E[d,m] by Parseval (SURVEY F2), identical estimate / shift / bits, "
+                    "no (peak, bin, offset) output", "shift_checksum": ck}
+        del demv
+
     # ---- e2e through the reference-facing class, host buffers ----
     e2e_steps = args.e2e_steps or min(args.steps, 200)
     e2e = None
@@ -655,7 +682,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
         "launch_mode": "cuda_graph" if world == 1 else ("eager, NVLink peer stores" if sh is not None else "eager + NCCL"),
         "chunks_in_flight": (K if world == 1 else 1),
-        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum,
+        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum, "variants": variants,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -203,7 +203,7 @@ class Engine:
     """Thin object wrapper over one ``pcs_handle`` (one CUDA stream, one pinned chunk buffer)."""
 
     def __init__(self, *, device, nfft, num_dopplers, element_offset, shifts, masks, window_width, sum_all_masks,
-                 code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5, use_graph=True, groups_per_cta=0):
+                 code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5, use_graph=True, groups_per_cta=0, xb_smem=False):
         self.lib = load()
         shifts = np.ascontiguousarray(shifts, dtype=np.int32)
         masks = np.ascontiguousarray(masks, dtype=np.complex64)
@@ -215,6 +215,7 @@ class Engine:
                      int(bool(sum_all_masks)), code_search_mask_offset, samples_per_sym, path, log2_block, snr_window)
         cfg.reserved[0] = 0 if use_graph else 1      # bit 0: do not capture the per-chunk sequence in a CUDA graph
         cfg.reserved[1] = int(groups_per_cta)        # tuning knob of the 256-point search kernel (0 = default)
+        cfg.reserved[2] = int(bool(xb_smem))         # tuning knob: block spectrum in shared memory instead of registers
         self._h = _P()
         self.nfft, self.D, self.M = nfft, num_dopplers + element_offset, masks.shape[0]
         self._check(self.lib.pcs_create(C.byref(cfg), _ptr(shifts), _ptr(masks), C.byref(self._h)))

@@ -262,6 +262,19 @@ PCS_DEVINL void os256_filter(const Os256Params& p, int m, const float2* xb, floa
     fft256_regs<+1>(v, buf, tw, t);
 }
 
+// Same with the block spectrum parked in shared memory ([r][16 lanes] float2) instead of 32 registers per lane.
+PCS_DEVINL void os256_filter_smem(const Os256Params& p, int m, const float2* xbs, float2* buf, const float2* tw, int t,
+                                  float2* v) {
+    const float4* __restrict__ g4 = p.gperm + (size_t)m * 128 + t;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const float4 g = __ldg(&g4[rr * 16]);
+        v[2 * rr] = cmul(xbs[(2 * rr) * 16 + t], make_float2(g.x, g.y));
+        v[2 * rr + 1] = cmul(xbs[(2 * rr + 1) * 16 + t], make_float2(g.z, g.w));
+    }
+    fft256_regs<+1>(v, buf, tw, t);
+}
+
 PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, int t) {
     unsigned vm = 0;
 #pragma unroll
@@ -272,9 +285,11 @@ PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, 
     return vm;
 }
 
-template <int G>     // groups (half warps) per CTA
-__global__ void __launch_bounds__(G * 16, 32 / G) search_os256_kernel(Os256Params p) {
+// XBS: keep the block spectrum in shared memory (fewer registers -> more resident warps) instead of registers.
+template <int G, bool XBS>     // G = groups (half warps) per CTA
+__global__ void __launch_bounds__(G * 16, XBS ? 40 / G : 32 / G) search_os256_kernel(Os256Params p) {
     __shared__ float2 sbuf[G][272];
+    __shared__ float2 sxb[XBS ? G : 1][XBS ? 256 : 1];
     extern __shared__ float s_acc[];          // [G groups][2][M][17]: per-lane sum / max of every mask
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
@@ -291,11 +306,17 @@ __global__ void __launch_bounds__(G * 16, 32 / G) search_os256_kernel(Os256Param
     const Os256Item it = os256_item(p, item);
     float2 xb[16];
     os256_block_spectrum(p, it, buf, tw, t, xb);
+    if (XBS) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sxb[XBS ? g : 0][(XBS ? r * 16 + t : 0)] = xb[r];
+        __syncwarp();
+    }
     const unsigned vm = os256_valid_mask(p, it, t);
 #pragma unroll 1
     for (int m = 0; m < p.M; ++m) {
         float2 v[16];
-        os256_filter(p, m, xb, buf, tw, t, v);
+        if (XBS) os256_filter_smem(p, m, sxb[XBS ? g : 0], buf, tw, t, v);
+        else os256_filter(p, m, xb, buf, tw, t, v);
         float sum = 0.f, best = 0.f;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
@@ -605,10 +626,11 @@ __global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
         }
         if (tid == 0) {
             const int i = s_pki[0];
-            p.res->peak_val = s_pk[0];
-            p.res->peak_bin = i / p.M;
-            p.res->peak_mask = i % p.M;
-            p.res->peak_offset = p.peak_off[i];
+            const bool have = i != 0x7fffffff;            // false for the Parseval variant (no surface, no peak)
+            p.res->peak_val = have ? s_pk[0] : -1.f;
+            p.res->peak_bin = have ? i / p.M : -1;
+            p.res->peak_mask = have ? i % p.M : -1;
+            p.res->peak_offset = have ? p.peak_off[i] : -1;
         }
     }
     __syncthreads();
@@ -994,6 +1016,85 @@ __global__ void centres_kernel(const float* __restrict__ ymag, const DevResult* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Parseval variant of the search metric -- a LABELLED alternative, never the default:
+//   E[d,m] = sum_n |y[d,m,n]|^2 / 2^18 = (N / 2^18) * sum_k |X[(k+s_d) % N]|^2 * |Mk[m,k]|^2
+// needs no inverse transform at all (and yields no peak / offsets).  W holds |Mk|^2 (or, in SUM mode, its sum over
+// the masks: one row).  One warp per (256-bin spectrum tile, Doppler-bin slice): the lane keeps its 8 x MW weights
+// in registers and walks the Doppler bins; partials [tile][D][MW] are reduced in a fixed order afterwards.
+// ---------------------------------------------------------------------------------------------
+__global__ void abs2_kernel(const float2* __restrict__ X, float* __restrict__ PX, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) PX[i] = cabs2(X[i]);
+}
+
+template <int MW>
+__global__ void __launch_bounds__(256) parseval_energy_kernel(const float* __restrict__ PX, const float* __restrict__ W,
+                                                              const int* __restrict__ shifts, float* __restrict__ part,
+                                                              int N, int D, int d_per_warp) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int ntile = N >> 8;
+    const int tile = warp % ntile, dslice = warp / ntile;
+    const int d0 = dslice * d_per_warp, d1 = min(D, d0 + d_per_warp);
+    if (d0 >= D) return;
+    const int k0 = tile << 8;
+    float w[8][MW];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int m = 0; m < MW; ++m) w[j][m] = __ldg(&W[(size_t)m * N + k0 + lane + 32 * j]);
+    const uint32_t nmask = (uint32_t)N - 1u;
+    for (int d = d0; d < d1; ++d) {
+        const uint32_t s = (uint32_t)shifts[d];
+        float acc[MW];
+#pragma unroll
+        for (int m = 0; m < MW; ++m) acc[m] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float px = __ldg(&PX[((uint32_t)(k0 + lane + 32 * j) + s) & nmask]);
+#pragma unroll
+            for (int m = 0; m < MW; ++m) acc[m] = fmaf(px, w[j][m], acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < MW; ++m) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < MW; ++m) part[((size_t)tile * D + d) * MW + m] = acc[m];
+        }
+    }
+}
+
+// Fixed-order sum over the tiles; scale N / 2^18.  Writes columns [0, MW) of rows with stride M (the pointers are
+// already offset to the batch's first column) and clears `extra` further columns (SUM mode: only column 0 is used).
+__global__ void parseval_reduce_kernel(const float* __restrict__ part, int ntile, int D, int MW, int M, int extra,
+                                       float scale, float* __restrict__ Efull, float* __restrict__ peak_val,
+                                       int* __restrict__ peak_off) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;      // (d, mw)
+    if (col >= D * MW) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int t = 0;
+    for (; t + 3 < ntile; t += 4) {
+        s0 += part[(size_t)t * D * MW + col];
+        s1 += part[(size_t)(t + 1) * D * MW + col];
+        s2 += part[(size_t)(t + 2) * D * MW + col];
+        s3 += part[(size_t)(t + 3) * D * MW + col];
+    }
+    for (; t < ntile; ++t) s0 += part[(size_t)t * D * MW + col];
+    const int d = col / MW, m = col % MW;
+    Efull[(size_t)d * M + m] = ((s0 + s1) + (s2 + s3)) * scale;
+    peak_val[(size_t)d * M + m] = -1.f;        // this variant has no correlation surface, hence no peak
+    peak_off[(size_t)d * M + m] = -1;
+    if (m == MW - 1)
+        for (int mm = MW; mm < MW + extra; ++mm) {
+            Efull[(size_t)d * M + mm] = 0.f;
+            peak_val[(size_t)d * M + mm] = -1.f;
+            peak_off[(size_t)d * M + mm] = -1;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Peer exchange (bin sharding over NVLink): arrival flags in the owner's exchange region.
 // ---------------------------------------------------------------------------------------------
 __global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {
@@ -1020,6 +1121,16 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int world, uns
     const unsigned all_ok = __all_sync(0xffffffffu, ok);
     if (r == 0) res->xchg_timeout = all_ok ? 0 : 1;
     __threadfence_system();
+}
+
+// computeSNR windows straight from a full spectrum (used when one is available anyway: Parseval variant).
+__global__ void spectrum_gather_kernel(const float2* __restrict__ X, int N, const DevResult* __restrict__ res,
+                                       float2* __restrict__ sig_win, float2* __restrict__ noise_win) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int len = res->sig_len;
+    if (i >= len) return;
+    sig_win[i] = X[(res->sig_start + i) & (N - 1)];
+    noise_win[i] = X[(res->noise_start + i) & (N - 1)];
 }
 
 // fp32 FMA peak probe: 16 independent FMA chains per thread.

@@ -88,6 +88,10 @@ struct pcs_handle {
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
     int* d_part_blk = nullptr;
     float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
+    // Parseval variant (labelled alternative: energies only, no peak)
+    bool parseval = false;
+    int pv_mw = 0;                     // weight rows: 1 in SUM mode, else M
+    float *d_W = nullptr, *d_PX = nullptr, *d_pvpart = nullptr;
     bool spectrum_full = false;        // d_X holds the full spectrum of the current chunk (computed on demand)
     // CUDA graph of the per-chunk sequence search -> estimate -> demod -> result copies (captured after one eager run)
     cudaGraphExec_t gexec = nullptr;
@@ -422,6 +426,38 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
     return 0;
 }
 
+template <int MW>
+static void launch_parseval_energy(pcs_handle* h, const float* W, const int* shifts, int Dl, int d_per_warp, int nslice) {
+    const int ntile = h->N >> 8;
+    const long long warps = (long long)ntile * nslice;
+    parseval_energy_kernel<MW><<<(unsigned)((warps + 7) / 8), 256, 0, h->stream>>>(h->d_PX, W, shifts, h->d_pvpart, h->N, Dl,
+                                                                                    d_per_warp);
+    h->launches++;
+}
+
+static int plan_parseval(pcs_handle* h, const float* masks_host) {
+    const int N = h->N, M = h->M, D = h->D;
+    h->pv_mw = h->cfg.sum_all_masks ? 1 : M;
+    const float2* mk = reinterpret_cast<const float2*>(masks_host);
+    std::vector<float> W((size_t)h->pv_mw * N);
+    for (int k = 0; k < N; ++k) {
+        double sum = 0;
+        for (int m = 0; m < M; ++m) {
+            const float2 v = mk[(size_t)m * N + k];
+            const double p = (double)v.x * v.x + (double)v.y * v.y;
+            if (h->pv_mw == 1) sum += p; else W[(size_t)m * N + k] = (float)p;
+        }
+        if (h->pv_mw == 1) W[k] = (float)sum;
+    }
+    if (int rc = dev_alloc(h, &h->d_W, W.size())) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->d_W, W.data(), sizeof(float) * W.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (int rc = dev_alloc(h, &h->d_PX, (size_t)N)) return rc;
+    if (int rc = dev_alloc(h, &h->d_pvpart, (size_t)(N >> 8) * D * std::min(h->pv_mw, 8))) return rc;
+    h->parseval = true;
+    return 0;
+}
+
 // ---- public API -----------------------------------------------------------------------------------
 extern "C" {
 
@@ -546,7 +582,10 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
 
     if (int rc = measure_support(h, &h->Lpos, &h->Lneg)) return rc;
     const int want = cfg->path;
-    if (want == PCS_PATH_AUTO || want == PCS_PATH_OVERLAP_SAVE) {
+    if (want == PCS_PATH_FULL)
+        return fail(PCS_ERR_INVALID, "PCS_PATH_FULL (Nfft-point inverse transforms) is not built: overlap-save gives the same "
+                                     "numbers for every filter support up to 2^13 taps");
+    if (want == PCS_PATH_AUTO || want == PCS_PATH_OVERLAP_SAVE || want == PCS_PATH_PARSEVAL) {
         int rc = plan_overlap_save(h, masks);
         if (rc == 0) {
             h->path = PCS_PATH_OVERLAP_SAVE;
@@ -560,6 +599,10 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (h->path == 0)
         return fail(PCS_ERR_INVALID, "path %d is not available in this build for a filter support of %d + %d taps",
                     want, h->Lpos, h->Lneg);
+    if (want == PCS_PATH_PARSEVAL) {
+        if (int rc = plan_parseval(h, masks)) return rc;
+        h->path = PCS_PATH_PARSEVAL;
+    }
     if (cfg->log2_block == 0 || cfg->log2_block == 8) {
         int rc = plan_fast256(h, masks);
         if (rc != 0 && rc != PCS_ERR_INVALID) return rc;
@@ -635,15 +678,19 @@ static int enqueue_search_local256(pcs_handle* h) {
     {
         StageTimer t(h, PCS_STAGE_SEARCH);
         const long long items = (long long)p.nblk * Dl;
-        const int G = h->cfg.reserved[1] == 16 ? 16 : 8;     // groups per CTA (tuning knob; 8 = default: measured 3 % faster)
+        const int G = h->cfg.reserved[1] == 16 ? 16 : h->cfg.reserved[1] == 4 ? 4 : 8;   // groups per CTA (8: measured best)
         h->search_ctas = (int)((items + G - 1) / G);
         const size_t acc_bytes = (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + acc_bytes);
-        static size_t configured[2] = {0, 0};          // static + dynamic shared memory may exceed the 48 KB default
-        auto kern = G == 8 ? search_os256_kernel<8> : search_os256_kernel<16>;
-        if (configured[G == 8] < acc_bytes) {
+        static size_t configured[6] = {0, 0, 0, 0, 0, 0};   // static + dynamic shared memory may exceed the 48 KB default
+        const bool xbs = h->cfg.reserved[2] == 1 && G != 16;   // tuning knob: block spectrum in shared memory
+        const int gi = (G == 16 ? 0 : G == 8 ? 1 : 2) + (xbs ? 3 : 0);
+        auto kern = xbs ? (G == 8 ? search_os256_kernel<8, true> : search_os256_kernel<4, true>)
+                        : (G == 16 ? search_os256_kernel<16, false> : G == 8 ? search_os256_kernel<8, false>
+                                                                              : search_os256_kernel<4, false>);
+        if (configured[gi] < acc_bytes) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-            configured[G == 8] = acc_bytes;
+            configured[gi] = acc_bytes;
         }
         kern<<<h->search_ctas, G * 16, acc_bytes, h->stream>>>(p);
         h->launches++;
@@ -663,7 +710,43 @@ static int enqueue_search_local256(pcs_handle* h) {
     return 0;
 }
 
+static int enqueue_search_local_parseval(pcs_handle* h) {
+    const int Dl = h->bin_hi - h->bin_lo, M = h->M, N = h->N;
+    const size_t row0 = (size_t)h->bin_lo * M;
+    StageTimer t(h, PCS_STAGE_SEARCH);
+    if (!h->spectrum_full) {
+        if (int rc = fft_large<-1>(h, LoadC{h->d_x_cur}, h->d_X)) return rc;
+        h->spectrum_full = true;
+    }
+    abs2_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(h->d_X, h->d_PX, N);
+    h->launches++;
+    const int d_per_warp = 32, nslice = (Dl + d_per_warp - 1) / d_per_warp;
+    const float scale = (float)N / 262144.0f;                     // kern:442 with Parseval's factor N
+    for (int m0 = 0; m0 < h->pv_mw;) {
+        const int rem = h->pv_mw - m0, mw = rem >= 8 ? 8 : rem >= 4 ? 4 : rem >= 2 ? 2 : 1;
+        const float* W = h->d_W + (size_t)m0 * N;
+        const int* sh = h->d_shifts + h->bin_lo;
+        switch (mw) {
+            case 8: launch_parseval_energy<8>(h, W, sh, Dl, d_per_warp, nslice); break;
+            case 4: launch_parseval_energy<4>(h, W, sh, Dl, d_per_warp, nslice); break;
+            case 2: launch_parseval_energy<2>(h, W, sh, Dl, d_per_warp, nslice); break;
+            default: launch_parseval_energy<1>(h, W, sh, Dl, d_per_warp, nslice); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        // the last batch also zero-fills the columns SUM mode leaves empty
+        const bool last = m0 + mw >= h->pv_mw;
+        parseval_reduce_kernel<<<(Dl * mw + 255) / 256, 256, 0, h->stream>>>(
+            h->d_pvpart, N >> 8, Dl, mw, M, last ? M - (m0 + mw) : 0, scale, h->tab_E + row0 + m0, h->tab_pv + row0 + m0,
+            h->tab_po + row0 + m0);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        m0 += mw;
+    }
+    return 0;
+}
+
 static int enqueue_search_local(pcs_handle* h) {
+    if (h->parseval) return enqueue_search_local_parseval(h);
     if (h->fast256) return enqueue_search_local256(h);
     const int Dl = h->bin_hi - h->bin_lo;
     const size_t row0 = (size_t)h->bin_lo * h->M;
@@ -709,6 +792,13 @@ static int enqueue_estimate_kernel(pcs_handle* h) {
 }
 
 static int enqueue_snr_bins(pcs_handle* h) {
+    if (h->spectrum_full) {        // a full spectrum of this chunk exists (Parseval variant): just gather the windows
+        spectrum_gather_kernel<<<(h->win_cap + 255) / 256, 256, 0, h->stream>>>(h->d_X, h->N, h->d_res, h->d_sigwin,
+                                                                             h->d_noisewin);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const float2* tw2 = nullptr;
     if (int rc = get_twiddles(h, h->logN2, &tw2)) return rc;
     spectrum_bins_kernel<<<(2 * h->win_cap + 7) / 8, 256, 0, h->stream>>>(h->d_scratch, tw2, 1 << h->logN1, 1 << h->logN2,
@@ -719,10 +809,10 @@ static int enqueue_snr_bins(pcs_handle* h) {
 }
 
 static int enqueue_estimate(pcs_handle* h) {
-    if (h->spectrum_pending) {
+    if (h->spectrum_pending && !h->spectrum_full) {
         if (int rc = enqueue_spectrum(h)) return rc;
-        h->spectrum_pending = false;
     }
+    h->spectrum_pending = false;
     StageTimer t2(h, PCS_STAGE_ESTIMATE);
     if (int rc = enqueue_estimate_kernel(h)) return rc;
     return enqueue_snr_bins(h);
@@ -844,10 +934,13 @@ static int enqueue_chunk_forked(pcs_handle* h) {
     cudaStream_t main_s = h->stream;
     CUDA_TRY(cudaEventRecord(h->ev_fork, main_s));
     CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    h->stream = h->side;
-    int rc = enqueue_spectrum(h);
-    h->stream = main_s;
-    if (rc) return rc;
+    int rc = 0;
+    if (!h->parseval) {            // (the Parseval variant computes the full spectrum on the main branch anyway)
+        h->stream = h->side;
+        rc = enqueue_spectrum(h);
+        h->stream = main_s;
+        if (rc) return rc;
+    }
     if ((rc = enqueue_search_local(h))) return rc;
     if ((rc = enqueue_estimate_kernel(h))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_est, main_s));

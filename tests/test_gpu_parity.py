@@ -291,3 +291,36 @@ def test_snr_matches_oracle_on_a_stream():
     for (fa, fb, _, _, _, _) in _run_both(dem, orc, sig):
         np.testing.assert_allclose(fa[3], fb[3], rtol=2e-4, atol=2e-4, equal_nan=True)
         np.testing.assert_allclose(fa[1], fb[1], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("cfg,blockSize,sum_all", [("benchmark/bench_GMSK.json", 15, True), ("benchmark/bench_GMSK.json", 14, False),
+                                                   ("CC11xx.json", 16, True), ("benchmark/bench_BPSK.json", 13, False)])
+def test_parseval_variant_matches_surface_energies(cfg, blockSize, sum_all):
+    """The labelled Parseval variant: same energies as the correlation-surface path without any inverse
+    transform, hence the same Doppler estimate, shift and demodulated bits; it reports no peak."""
+    from pycusdr_b200 import _native
+    from pycusdr_b200.demodulator import UHF
+    conf = conf_variant(cfg, blockSize=blockSize)
+    P = protocol_for(conf)
+    P.SUM_ALL_MASKS_PYTHON = sum_all
+    demP = UHF.Demodulator(conf, P, RADIO, path=_native.PATH_PARSEVAL)
+    demS = UHF.Demodulator(conf, P, RADIO)
+    orc = O.OracleDemodulator(conf, P, RADIO)
+    assert demP._engine.plan()["path"] == _native.PATH_PARSEVAL
+    sps = conf["Radios"]["Rx"][RADIO]["samplesPerSym"]
+    N = 2 ** blockSize
+    for seed in (5, 6, 7):                          # several chunks: the second one on replays the CUDA graph
+        x = _noise_chunk(N, seed, with_packet="GMSK" if sps == 16 else None, sps=sps)
+        for d in (demP, demS):
+            d.get_signalBufferHostPointer()[:] = x
+        fp = demP.uploadAndFindCarrier(demP.get_signalBufferHostPointer())
+        fs = demS.uploadAndFindCarrier(demS.get_signalBufferHostPointer())
+        bp, bs = demP.demodulate(), demS.demodulate()
+        Eo = O.search_energy_parseval(O.forward_fft(x), orc.masks, orc.doppCyperSymNorm, sum_all)
+        assert rel_err(demP.last["E"], Eo) < 2e-5
+        assert rel_err(demP.last["E"], demS.last["E"]) < 1e-4
+        assert demP.last["shift"] == demS.last["shift"]
+        assert fp[0] == pytest.approx(fs[0], abs=1e-2)
+        np.testing.assert_allclose(fp[3], fs[3], rtol=1e-4, atol=1e-4, equal_nan=True)      # SNR: gathered vs pruned bins
+        np.testing.assert_array_equal(bp[0], bs[0])
+        assert demP.last["peak"] == (-1.0, -1, -1, -1)
