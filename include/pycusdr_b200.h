@@ -222,6 +222,23 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
 int pcs_stitch_reset(pcs_stitcher* s);
 int pcs_stitch_destroy(pcs_stitcher* s);
 
+/* Native sample ingest: what the reference's SigFIFO ring buffer (sigFIFO.py:13-181) and the chunk loop of
+ * demodulator_process.py:284-338 do on the host, as a pipeline.  Samples are pushed in arbitrary block sizes; every
+ * nfft - overlap new samples become a chunk whose first `overlap` samples are carried over from the previous chunk ON
+ * THE DEVICE; the H2D copy of a chunk overlaps the kernels of the chunks before it; chunks go round-robin to the
+ * `n_handles` handles (all created with the same configuration), results are popped in chunk order.  Per-chunk results
+ * are identical to pcs_upload + pcs_process on the same samples.  pcs_ingest_push may block while the oldest chunk of a
+ * handle is still running (back-pressure); pcs_ingest_pop(block = 0) never blocks.  sig_win / noise_win receive the
+ * computeSNR windows (complex64[res->sig_len] each, see pcs_snr_windows). */
+typedef struct pcs_ingest pcs_ingest;
+int pcs_ingest_create(pcs_handle* const* handles, int32_t n_handles, int32_t nfft, int32_t overlap, int32_t num_bins,
+                      int32_t num_masks, int32_t device, pcs_ingest** out);
+int pcs_ingest_push(pcs_ingest* s, const void* samples /* complex64[n] */, int64_t n, int32_t* chunks_submitted);
+int pcs_ingest_pop(pcs_ingest* s, int32_t block, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag,
+                   float* sig_win, float* noise_win, int32_t* ready);
+int pcs_ingest_pending(const pcs_ingest* s, int64_t* submitted, int64_t* popped);
+int pcs_ingest_destroy(pcs_ingest* s);
+
 const char* pcs_last_error(void);
 int pcs_abi_version(void);
 

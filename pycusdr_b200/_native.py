@@ -85,6 +85,11 @@ SYMBOLS = {
     "pcs_stitch_chunk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_stitch_reset": (C.c_int, [_P]),
     "pcs_stitch_destroy": (C.c_int, [_P]),
+    "pcs_ingest_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "pcs_ingest_push": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
+    "pcs_ingest_pop": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
+    "pcs_ingest_pending": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pcs_ingest_destroy": (C.c_int, [_P]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -191,6 +196,70 @@ class Stitcher:
         if h is not None and h.value:
             self._h = None
             self.lib.pcs_stitch_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ingest:
+    """Native sample ingest over several engines (``pcs_ingest_*``): push samples in any block size, pop per-chunk
+    results in order.  The engines must share one configuration and outlive this object."""
+
+    def __init__(self, engines, nfft, overlap, device=0):
+        self.lib = load()
+        self.engines = list(engines)
+        e0 = self.engines[0]
+        self.D, self.M, self.max_sym = e0.D, e0.M, e0.max_sym
+        arr = (_P * len(self.engines))(*[e._h for e in self.engines])
+        self._h = _P()
+        rc = self.lib.pcs_ingest_create(arr, len(self.engines), int(nfft), int(overlap), self.D, self.M, int(device),
+                                        C.byref(self._h))
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+        _live.add(self)
+        self._E = np.empty((self.D, self.M), dtype=np.float32)
+        self._sym = np.empty(self.max_sym, dtype=np.int32)
+        self._centre = np.empty(self.max_sym, dtype=np.int32)
+        self._mag = np.empty(self.max_sym, dtype=np.float32)
+        self._sig = np.empty(8192, dtype=np.complex64)
+        self._noise = np.empty(8192, dtype=np.complex64)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+
+    def push(self, samples):
+        """Append samples; returns the number of chunks this call completed and submitted."""
+        samples = np.ascontiguousarray(samples, dtype=np.complex64)
+        n = C.c_int32(0)
+        self._check(self.lib.pcs_ingest_push(self._h, _ptr(samples), len(samples), C.byref(n)))
+        return n.value
+
+    def pop(self, block=True):
+        """Next chunk's results ``(res, E, sym, centre, mag, sig_win, noise_win)`` (copies), or None if none is ready."""
+        res, ready = Result(), C.c_int32(0)
+        self._check(self.lib.pcs_ingest_pop(self._h, int(bool(block)), C.byref(res), _ptr(self._E), _ptr(self._sym),
+                                            _ptr(self._centre), _ptr(self._mag), _ptr(self._sig), _ptr(self._noise),
+                                            C.byref(ready)))
+        if not ready.value:
+            return None
+        n, w = res.n_sym, max(res.sig_len, 0)
+        return (res, self._E.copy(), self._sym[:n].copy(), self._centre[:n].copy(), self._mag[:n].copy(),
+                self._sig[:w].copy(), self._noise[:w].copy())
+
+    def pending(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.pcs_ingest_pending(self._h, C.byref(a), C.byref(b)))
+        return a.value - b.value
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = None
+            self.lib.pcs_ingest_destroy(h)
 
     def __del__(self):
         try:

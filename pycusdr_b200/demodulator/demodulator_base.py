@@ -118,12 +118,13 @@ class Demodulator:
         self.codeRateAndPhaseOffsetHigh = int(self.Nfft / self.symsTolHigh)
 
         # device side: raises (no CPU fallback) if the library or a GPU is missing
-        self._engine = _native.Engine(
+        self._engine_kwargs = dict(
             device=confGPU["CUDA"]["device"], nfft=self.Nfft, num_dopplers=self.num_dopplers,
             element_offset=self.doppIdxArrayOffset, shifts=self.doppCyperSymNorm, masks=masks,
             window_width=self.windowWidth, sum_all_masks=self.SUM_ALL_MASKS_PYTHON,
             code_search_mask_offset=self.CODE_SEARCH_MASK_OFFSET, samples_per_sym=self.spsym, path=path,
             log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph, groups_per_cta=groups_per_cta, xb_smem=xb_smem)
+        self._engine = _native.Engine(**self._engine_kwargs)
         self.GPU_bufSignalTime_cpu_handle = self._engine.host_buffer
         # bit extraction + chunk stitching + trust tagging in one native call (the NumPy methods below stay as the
         # readable mirror of dem_base:863-1051 and are what ``native_post=False`` runs)
@@ -188,6 +189,10 @@ class Demodulator:
         else:
             res, E = eng.search()
             self._pending = None
+        return self._finish_search(res, E)
+
+    def _finish_search(self, res, E, wins=None):
+        """Host half of __findUHF (dem_base:604-632) on the device results of one chunk."""
         self.last = {"E": E.copy(), "res": np.array([res.best_idx, res.metric_db], dtype=np.float32),
                      "peak": (res.peak_val, res.peak_bin, res.peak_mask, res.peak_offset)}
         if res.status != 0:          # NaN estimate: the reference's ValueError branch (dem_base:625-630)
@@ -199,13 +204,13 @@ class Demodulator:
         lowVal, highVal = self.doppHzLUT[lowIdx], self.doppHzLUT[highIdx]
         bestDopplerScaled = lowVal + (highVal - lowVal) * frac
         self.dopplerIdxlast = np.int32(res.shift)
-        SNR = self.computeSNR(lowIdx, highIdx, SNR_WINDOW, res)
+        SNR = self.computeSNR(lowIdx, highIdx, SNR_WINDOW, res, wins)
         freqOffset = bestDopplerScaled - self.centreFreqOffset
         sdev_Hz = np.float64(res.metric_db) / self.Nfft * self.sampleRate
         return freqOffset, sdev_Hz, self.clippedPeakIPure, SNR
 
     # -- a10 -------------------------------------------------------------------------------------
-    def computeSNR(self, doppMatchLow, doppMatchHigh, windowWidth, res=None):
+    def computeSNR(self, doppMatchLow, doppMatchHigh, windowWidth, res=None, given=None):
         """SNR from the chunk spectrum around the found bins vs the same window half a band away
         (dem_base:635-667), evaluated with the reference's slicing rules on windows the device gathered."""
         N = self.Nfft
@@ -214,7 +219,7 @@ class Demodulator:
         nlo, nhi = (lo + N // 2) % N, (hi + N // 2) % N
         wins = None
         if res is not None and res.sig_len > 0 and windowWidth == SNR_WINDOW:
-            sig, noise = self._engine.snr_windows(res)
+            sig, noise = given if given is not None else self._engine.snr_windows(res)
             # common case: neither window touches the ends of the spectrum, so the reference's slices
             # X[a-w : b+w] are exactly the two windows the device gathered (dem_base:657-661)
             w = windowWidth
