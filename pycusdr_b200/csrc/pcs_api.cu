@@ -16,6 +16,7 @@
 
 using namespace pcs;
 
+#define PCS_MAX_DEVICES 64
 static thread_local std::string g_last_error;
 
 static int fail(int code, const char* fmt, ...) {
@@ -194,10 +195,10 @@ static int launch_tile_t(pcs_handle* h, const TileGeom& g, Load ld, Store st) {
     if (int rc = get_twiddles(h, LOGB, &tw)) return rc;
     const size_t smem = (size_t)2 * C * S::WORK * sizeof(float2);
     auto kern = fft_tile_kernel<LOGB, DIR, C, Load, Store>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static bool configured[PCS_MAX_DEVICES] = {};   // per instantiation and device (the attribute is per device)
+    if (!configured[h->cfg.device]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[h->cfg.device] = true;
     }
     const int grid = (g.nvec + C - 1) / C;
     kern<<<grid, C * S::T, smem, h->stream>>>(g, tw, ld, st);
@@ -272,10 +273,10 @@ static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p) {
     constexpr int NW = (S::T + 31) / 32;
     const size_t smem = (size_t)G * 3 * S::WORK * sizeof(float2) + (size_t)G * p.M * NW * 3 * sizeof(float);
     auto kern = search_os_kernel<LOGB, G>;
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[PCS_MAX_DEVICES] = {};
+    if (configured[h->cfg.device] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[h->cfg.device] = smem;
     }
     const long long items = (long long)p.nblk * p.D;
     const int grid = (int)((items + G - 1) / G);
@@ -292,10 +293,10 @@ static int launch_demod_os_t(pcs_handle* h, const OsDemodParams& p) {
     using S = FftShape<LOGB>;
     const size_t smem = (size_t)G * 3 * S::WORK * sizeof(float2);
     auto kern = demod_os_kernel<LOGB, G>;
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[PCS_MAX_DEVICES] = {};
+    if (configured[h->cfg.device] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[h->cfg.device] = smem;
     }
     const int grid = (p.nblk + G - 1) / G;
     kern<<<grid, G * S::T, smem, h->stream>>>(p);
@@ -504,6 +505,7 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(PCS_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (cfg->device >= PCS_MAX_DEVICES) return fail(PCS_ERR_INVALID, "device index %d too large", cfg->device);
     if (cfg->device < 0 || cfg->device >= ndev) return fail(PCS_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
     CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
@@ -682,15 +684,15 @@ static int enqueue_search_local256(pcs_handle* h) {
         h->search_ctas = (int)((items + G - 1) / G);
         const size_t acc_bytes = (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + acc_bytes);
-        static size_t configured[6] = {0, 0, 0, 0, 0, 0};   // static + dynamic shared memory may exceed the 48 KB default
+        static size_t configured[PCS_MAX_DEVICES][6] = {};   // static + dynamic shared memory may exceed the 48 KB default
         const bool xbs = h->cfg.reserved[2] == 1 && G != 16;   // tuning knob: block spectrum in shared memory
         const int gi = (G == 16 ? 0 : G == 8 ? 1 : 2) + (xbs ? 3 : 0);
         auto kern = xbs ? (G == 8 ? search_os256_kernel<8, true> : search_os256_kernel<4, true>)
                         : (G == 16 ? search_os256_kernel<16, false> : G == 8 ? search_os256_kernel<8, false>
                                                                               : search_os256_kernel<4, false>);
-        if (configured[gi] < acc_bytes) {
+        if (configured[h->cfg.device][gi] < acc_bytes) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-            configured[gi] = acc_bytes;
+            configured[h->cfg.device][gi] = acc_bytes;
         }
         kern<<<h->search_ctas, G * 16, acc_bytes, h->stream>>>(p);
         h->launches++;
