@@ -425,9 +425,14 @@ def main():
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        sh = sharded.ShardedSearch(eng, rank, world, all_gather)
+        K = max(1, args.inflight)
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta,
+                                 xb_smem=args.xb_smem) for _ in range(K - 1)]
+        engs = [eng] + [d._engine for d in extra]
+        sh = sharded.ShardedPipelines(engs, rank, world, all_gather)
         lo, hi = sh.slices[rank]
-        timing_stream = torch.cuda.ExternalStream(eng.stream)
+        streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
+        timing_stream = streams[0]
     elif world > 1:   # bin sharding with NCCL all-gathers and a replicated tail (comparison variant)
         per = (D + world - 1) // world
         lo, hi = min(rank * per, D), min((rank + 1) * per, D)
@@ -477,23 +482,28 @@ def main():
         return int(out[0].shift) + int(out[2][:16].sum())
 
     if sh is not None:
-        warm = -(-max(args.warmup, world) // world) * world        # whole owner rounds
+        unit = world * K
+        warm = -(-max(args.warmup, unit) // unit) * unit          # whole owner rounds of every pipeline
         for i in range(warm):
             sh.enqueue(i, ptrs[i % ring], collect=consume)
         sh.drain(consume)
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        launches0 = eng.launch_count
+        launches0 = sum(e.launch_count for e in engs)
         sampler = ClockSampler(local)
         sampler.start()
-        ev0.record(timing_stream)
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
         for i in range(args.steps):
             sh.enqueue(warm + i, ptrs[(warm + i) % ring], collect=consume)
         sh.drain(consume)
-        ev1.record(timing_stream)
+        for st in streams[1:]:
+            streams[0].wait_stream(st)
+        ev1.record(streams[0])
         torch.cuda.synchronize()
-        launches = eng.launch_count - launches0
+        launches = sum(e.launch_count for e in engs) - launches0
         checksum = sum(v for k, v in sh.results.items() if k >= warm)
         ck = torch.tensor([checksum], device="cuda", dtype=torch.int64)
         dist.all_reduce(ck)
@@ -556,8 +566,8 @@ def main():
     #      (launched kernel by kernel; the timed region above replays them as one CUDA graph) ----
     eng.set_profiling(True)
     if sh is not None:
-        base = warm + args.steps
-        for i in range(world * max(4, min(args.steps, 64) // world)):
+        base = -(-(warm + args.steps) // unit) * unit
+        for i in range(unit * max(2, min(args.steps, 64) // unit)):
             sh.enqueue(base + i, ptrs[(base + i) % ring], collect=consume)
         sh.drain(consume)
     else:
@@ -707,7 +717,7 @@ def main():
                        f"doppler bins sharded over {world} GPUs + NCCL all-gather, replicated tail")},
         "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
         "launch_mode": "cuda_graph" if world == 1 else ("eager, NVLink peer stores" if sh is not None else "eager + NCCL"),
-        "chunks_in_flight": (K if world == 1 else 1),
+        "chunks_in_flight": (K if (world == 1 or sh is not None) else 1),
         "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "checksum": checksum, "variants": variants,
     }
     print(json.dumps(line))

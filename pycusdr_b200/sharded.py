@@ -79,6 +79,33 @@ class ShardedSearch:
         return self.results
 
 
+class ShardedPipelines:
+    """``P`` independent ``ShardedSearch`` pipelines per rank (one engine, pair of CUDA streams and exchange region
+    each): chunk ``c`` goes to pipeline ``c % P`` as its local chunk ``c // P``.  With P = 2 the search kernel of one
+    chunk fills the SMs that the last, partially filled wave and the reduction kernels of the previous chunk leave
+    idle -- the same "two chunks in flight" the single-GPU path uses."""
+
+    def __init__(self, engines, rank, world, all_gather):
+        self.pipes = [ShardedSearch(e, rank, world, all_gather) for e in engines]
+        self.rank, self.world = rank, world
+        self.slices = self.pipes[0].slices
+
+    def enqueue(self, chunk_no, chunk, collect=None):
+        P = len(self.pipes)
+        return self.pipes[chunk_no % P].enqueue(chunk_no // P, chunk, collect)
+
+    def drain(self, collect=None):
+        for p in self.pipes:
+            p.drain(collect)
+        return self.results
+
+    @property
+    def results(self):
+        """{global chunk number: result} of the chunks this rank owned."""
+        P = len(self.pipes)
+        return {q * P + j: r for j, p in enumerate(self.pipes) for q, r in p.results.items()}
+
+
 def gather_results(results, world, gather_object, rank):
     """Merge the per-rank ``{seq: result}`` dicts on rank 0, ordered by chunk. ``gather_object(obj)`` returns the
     list of all ranks' objects on rank 0 (``None`` elsewhere)."""

@@ -55,7 +55,8 @@ def _tail(orc, E, pv, po, x):
 
 
 class FakeEngine:
-    def __init__(self, rank, world):
+    def __init__(self, rank, world, pipe=0):
+        self.pipe = pipe
         conf = _conf()
         self.orc = O.OracleDemodulator(conf, protocol_for(conf), RADIO)
         self.D, self.M = len(self.orc.doppCyperSymNorm), self.orc.num_masks
@@ -90,7 +91,7 @@ class FakeEngine:
             t[0][self.lo:self.hi], t[1][self.lo:self.hi], t[2][self.lo:self.hi] = E, pv, po
         else:
             for k, a in enumerate((E, pv, po.view(np.float32))):
-                dist.send(torch.from_numpy(np.ascontiguousarray(a)), dst=owner, tag=seq * 4 + k)
+                dist.send(torch.from_numpy(np.ascontiguousarray(a)), dst=owner, tag=(seq * 4 + k) * 8 + self.pipe)
 
     def enqueue_owner_tail(self, seq):
         t = self.tables.pop(seq)
@@ -99,7 +100,7 @@ class FakeEngine:
                 continue
             for k in range(3):
                 buf = torch.empty((hi - lo, self.M), dtype=torch.float32)
-                dist.recv(buf, src=r, tag=seq * 4 + k)
+                dist.recv(buf, src=r, tag=(seq * 4 + k) * 8 + self.pipe)
                 t[k][lo:hi] = buf.numpy() if k < 2 else buf.numpy().view(np.int32)
         self.log.append(("tail", seq))
         self.out = _tail(self.orc, t[0], t[1], t[2], self.x)
@@ -110,7 +111,7 @@ class FakeEngine:
         return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, pipes=1):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         def all_gather(obj):
@@ -123,12 +124,16 @@ def _worker(rank, world, port, q):
             dist.gather_object(obj, out, dst=0)
             return out
 
-        eng = FakeEngine(rank, world)
-        sh = sharded.ShardedSearch(eng, rank, world, all_gather)
+        if pipes == 1:
+            sh = sharded.ShardedSearch(FakeEngine(rank, world), rank, world, all_gather)
+            want_owner = [s % world for s in range(N_CHUNKS)]
+        else:
+            sh = sharded.ShardedPipelines([FakeEngine(rank, world, j) for j in range(pipes)], rank, world, all_gather)
+            want_owner = [(s // pipes) % world for s in range(N_CHUNKS)]
         owners = [sh.enqueue(seq, x) for seq, x in enumerate(_chunks())]
         sh.drain()
-        assert owners == [s % world for s in range(N_CHUNKS)]
-        assert sorted(sh.results) == [s for s in range(N_CHUNKS) if s % world == rank]
+        assert owners == want_owner
+        assert sorted(sh.results) == [s for s in range(N_CHUNKS) if want_owner[s] == rank]
         merged = sharded.gather_results(sh.results, world, gather_object, rank)
         if rank == 0:
             q.put([{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in merged])
@@ -165,12 +170,13 @@ def test_out_of_order_chunks_are_rejected():
 
 
 @pytest.mark.timeout(300)
-def test_two_gloo_ranks_reproduce_the_single_process_result():
+@pytest.mark.parametrize("pipes", [1, 2])
+def test_two_gloo_ranks_reproduce_the_single_process_result(pipes):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, pipes)) for r in range(world)]
     for p in procs:
         p.start()
     merged = q.get(timeout=240)

@@ -44,8 +44,9 @@ def gather_object(obj):
     return out
 
 
-dem = UHF.Demodulator(conf, P, RADIO)
-sh = sharded.ShardedSearch(dem._engine, rank, world, all_gather)
+dems = [UHF.Demodulator(conf, P, RADIO) for _ in range(2)]
+dem = dems[0]
+sh = sharded.ShardedPipelines([d._engine for d in dems], rank, world, all_gather)
 for rep in range(2):                       # two passes: exercises both parities of the exchange region repeatedly
     for c in range(nchunks):
         sh.enqueue(rep * nchunks + c, chunks[c].data_ptr(), collect=collect)
@@ -72,6 +73,7 @@ if rank == 0:
     print(f"sharded check: world {world}, {len(merged)} chunks, {bad} mismatches")
     ok = bad == 0
 dist.barrier()
-dem._engine.close()
+for d in dems:
+    d._engine.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
