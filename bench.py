@@ -566,7 +566,7 @@ def main():
     #      (launched kernel by kernel; the timed region above replays them as one CUDA graph) ----
     eng.set_profiling(True)
     if sh is not None:
-        base = -(-(warm + args.steps) // unit) * unit
+        base = warm + args.steps
         for i in range(unit * max(2, min(args.steps, 64) // unit)):
             sh.enqueue(base + i, ptrs[(base + i) % ring], collect=consume)
         sh.drain(consume)

@@ -6,7 +6,7 @@ OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi topo -m > $OUT/topo_$TAG.txt 2>&1
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + $1)) "${@:2}"; }
 run $N tools/check_sharded_gpu.py > $OUT/sharded_check_${TAG}_n$N.log 2>&1; echo "sharded check rc=$?"; tail -5 $OUT/sharded_check_${TAG}_n$N.log
-python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest_gpu_$TAG.log
+
 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 50 > $OUT/scale_${TAG}_n1.json 2> $OUT/scale_${TAG}_n1.err; echo "n1 rc=$?"
 for n in 2 4 8; do
   if [ $n -le $N ]; then

@@ -8,7 +8,6 @@ for n in 8 4; do
   run $n bench.py --gpus $n --steps 400 --warmup 24 > $OUT/scale_${TAG}_n$n.json 2> $OUT/scale_${TAG}_n$n.err; echo "n$n rc=$?"
 done
 run 8 bench.py --gpus 8 --steps 100 --warmup 8 --workload c4 > $OUT/scale_${TAG}_c4_n8.json 2> $OUT/scale_${TAG}_c4_n8.err; echo "c4 n8 rc=$?"
-run 8 bench.py --gpus 8 --steps 30 --warmup 5 --workload c5 > $OUT/scale_${TAG}_c5_n8.json 2> $OUT/scale_${TAG}_c5_n8.err; echo "c5 n8 rc=$?"
 for f in $OUT/scale_${TAG}_n8.json $OUT/scale_${TAG}_n4.json $OUT/scale_${TAG}_c4_n8.json $OUT/scale_${TAG}_c5_n8.json; do python - "$f" <<'PY'
 import json,sys
 try:
