@@ -34,12 +34,14 @@ typedef enum {
     PCS_ERR_STATE = -4         /* call order violated (e.g. demod before a chunk was uploaded) */
 } pcs_status;
 
-/* Which formulation computes the (bins x masks x samples) correlation surface. All give the same
- * numbers to fp32 rounding (DESIGN.md "paths"):
- *   AUTO          overlap-save when the filters' time support is short enough, else full length
- *   OVERLAP_SAVE  blocks of B points, whole pipeline inside one SM's shared memory
- *   FULL          Nfft-point inverse transforms (two tiled passes, L2-resident scratch)
- *   PARSEVAL      energies only, no inverse transform (labelled variant, no peak / offsets)     */
+/* Which formulation computes the search metric:
+ *   AUTO / OVERLAP_SAVE  the (bins x masks x samples) correlation surface by overlap-save with B-point transforms that
+ *                        never leave the SM: 256-point register-resident blocks for filters up to 128 taps, 2^9..2^13
+ *                        shared-memory blocks for longer ones (up to 4096 taps); same numbers as Nfft-point inverse
+ *                        transforms to fp32 rounding
+ *   FULL                 reserved (Nfft-point inverse transforms); pcs_create rejects it in this build
+ *   PARSEVAL             labelled variant: energies by Parseval's theorem, no inverse transform, no peak / offsets
+ *                        (peak_* = -1); identical Doppler estimate, shift and demodulated bits                     */
 typedef enum { PCS_PATH_AUTO = 0, PCS_PATH_OVERLAP_SAVE = 1, PCS_PATH_FULL = 2, PCS_PATH_PARSEVAL = 3 } pcs_path;
 
 typedef struct {

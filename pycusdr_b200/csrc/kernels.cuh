@@ -1148,10 +1148,4 @@ __global__ void fma_peak_kernel(float* sink, int iters, float a, float b) {
     if (s == 12345.678f) sink[threadIdx.x & 4095] = s;
 }
 
-// Small helpers --------------------------------------------------------------------------------
-__global__ void real_to_complex_kernel(const float* __restrict__ in, float2* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_float2(in[i], 0.f);
-}
-
 }  // namespace pcs
