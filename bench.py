@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--xb-smem", action="store_true", help="tuning knob: block spectrum in shared memory")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=3,
                     help="chunks in flight for the device-resident figure (one handle + stream each; SURVEY 8(d) allows >= 2)")
     args = ap.parse_args()
 
