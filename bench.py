@@ -370,9 +370,11 @@ def main():
     ap.add_argument("--xb-smem", action="store_true", help="tuning knob: block spectrum in shared memory")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=0,
                     help="chunks in flight for the device-resident figure (one handle + stream each; SURVEY 8(d) allows >= 2)")
     args = ap.parse_args()
+    if args.inflight <= 0:      # measured: 3 handles in flight on one GPU, 2 sharded pipelines per rank on several
+        args.inflight = 3 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2
 
     if args.workload == "c5":
         return run_c5(args)
