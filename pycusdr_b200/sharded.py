@@ -75,6 +75,10 @@ class ShardedSearch:
         while self._owned:
             seq = self._owned.popleft()
             out = self.engine.fetch()
+            head = out[0] if isinstance(out, tuple) else out
+            if getattr(head, "xchg_timeout", 0):
+                raise RuntimeError(f"chunk {seq}: a peer's rows never reached rank {self.rank} (exchange timed out); "
+                                   "its results are not valid")
             self.results[seq] = collect(out) if collect is not None else out
         return self.results
 
