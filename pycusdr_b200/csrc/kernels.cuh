@@ -521,13 +521,13 @@ __global__ void __launch_bounds__(256) estimate_kernel(EstimateParams p) {
     __shared__ int s_pki[256];
     const int tid = threadIdx.x;
     // 1 + 2. reference layout of E and the per-column running top-2 (kern:527-544, one thread per column), staged
-    // through shared memory 64 bins at a time so that the serial scan runs at shared-memory latency.
-    __shared__ float tile[64][33];
+    // through shared memory 256 bins at a time so that the serial scan runs at shared-memory latency.
+    __shared__ float tile[256][33];
     const int ncols = p.sum_all ? 1 : p.M;
     float v0 = 0.f, v1 = 0.f;
     int i0 = 0, i1 = 0, cur = 0;
-    for (int base = 0; base < p.D; base += 64) {
-        const int rows = min(64, p.D - base);
+    for (int base = 0; base < p.D; base += 256) {
+        const int rows = min(256, p.D - base);
         if (p.sum_all) {
             if (tid < rows) {
                 const float* src = p.Efull + (size_t)(base + tid) * p.M;
@@ -1068,22 +1068,28 @@ __global__ void __launch_bounds__(256) parseval_energy_kernel(const float* __res
 
 // Fixed-order sum over the tiles; scale N / 2^18.  Writes columns [0, MW) of rows with stride M (the pointers are
 // already offset to the batch's first column) and clears `extra` further columns (SUM mode: only column 0 is used).
-__global__ void parseval_reduce_kernel(const float* __restrict__ part, int ntile, int D, int MW, int M, int extra,
-                                       float scale, float* __restrict__ Efull, float* __restrict__ peak_val,
-                                       int* __restrict__ peak_off) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;      // (d, mw)
-    if (col >= D * MW) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int t = 0;
-    for (; t + 3 < ntile; t += 4) {
-        s0 += part[(size_t)t * D * MW + col];
-        s1 += part[(size_t)(t + 1) * D * MW + col];
-        s2 += part[(size_t)(t + 2) * D * MW + col];
-        s3 += part[(size_t)(t + 3) * D * MW + col];
+__global__ void __launch_bounds__(1024) parseval_reduce_kernel(const float* __restrict__ part, int ntile, int D, int MW,
+                                                               int M, int extra, float scale, float* __restrict__ Efull,
+                                                               float* __restrict__ peak_val, int* __restrict__ peak_off) {
+    // block (32, 32): lane = column (d, mw), warp w sums tiles w, w + 32, ...; the 32 partials are added in warp order
+    __shared__ float s_sum[32][33];
+    const int col = blockIdx.x * 32 + threadIdx.x, w = threadIdx.y, cols = D * MW;
+    float s0 = 0.f, s1 = 0.f;
+    if (col < cols) {
+        int t = w;
+        for (; t + 32 < ntile; t += 64) {
+            s0 += part[(size_t)t * cols + col];
+            s1 += part[(size_t)(t + 32) * cols + col];
+        }
+        for (; t < ntile; t += 32) s0 += part[(size_t)t * cols + col];
     }
-    for (; t < ntile; ++t) s0 += part[(size_t)t * D * MW + col];
+    s_sum[w][threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (w != 0 || col >= cols) return;
+    float sum = s_sum[0][threadIdx.x];
+    for (int k = 1; k < 32; ++k) sum += s_sum[k][threadIdx.x];
     const int d = col / MW, m = col % MW;
-    Efull[(size_t)d * M + m] = ((s0 + s1) + (s2 + s3)) * scale;
+    Efull[(size_t)d * M + m] = sum * scale;
     peak_val[(size_t)d * M + m] = -1.f;        // this variant has no correlation surface, hence no peak
     peak_off[(size_t)d * M + m] = -1;
     if (m == MW - 1)

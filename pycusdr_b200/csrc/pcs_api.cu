@@ -737,7 +737,7 @@ static int enqueue_search_local_parseval(pcs_handle* h) {
         CUDA_TRY(cudaGetLastError());
         // the last batch also zero-fills the columns SUM mode leaves empty
         const bool last = m0 + mw >= h->pv_mw;
-        parseval_reduce_kernel<<<(Dl * mw + 255) / 256, 256, 0, h->stream>>>(
+        parseval_reduce_kernel<<<(Dl * mw + 31) / 32, dim3(32, 32), 0, h->stream>>>(
             h->d_pvpart, N >> 8, Dl, mw, M, last ? M - (m0 + mw) : 0, scale, h->tab_E + row0 + m0, h->tab_pv + row0 + m0,
             h->tab_po + row0 + m0);
         h->launches++;
