@@ -431,11 +431,26 @@ def main():
         extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta,
                                  xb_smem=args.xb_smem) for _ in range(K - 1)]
         engs = [eng] + [d._engine for d in extra]
-        sh = sharded.ShardedPipelines(engs, rank, world, all_gather)
-        lo, hi = sh.slices[rank]
-        streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
-        timing_stream = streams[0]
-    elif world > 1:   # bin sharding with NCCL all-gathers and a replicated tail (comparison variant)
+        p2p_error = None
+        try:
+            sh = sharded.ShardedPipelines(engs, rank, world, all_gather)
+        except Exception as e:        # e.g. CUDA IPC not permitted between these processes
+            sh, p2p_error = None, repr(e)
+        ok = torch.tensor([0 if sh is None else 1], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:       # every rank falls back together to the NCCL exchange on a fresh handle
+            if rank == 0:
+                print(f"bench: peer-memory exchange unavailable ({p2p_error}); using the NCCL all-gather path", file=sys.stderr)
+            sh = None
+            args.exchange = "nccl"
+            dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta,
+                                  xb_smem=args.xb_smem)
+            eng = dem._engine
+        else:
+            lo, hi = sh.slices[rank]
+            streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
+            timing_stream = streams[0]
+    if world > 1 and sh is None:   # bin sharding with NCCL all-gathers and a replicated tail (comparison variant / fallback)
         per = (D + world - 1) // world
         lo, hi = min(rank * per, D), min((rank + 1) * per, D)
         eng.set_bin_range(lo, max(hi, lo + 1))
@@ -463,7 +478,7 @@ def main():
             eng.enqueue_estimate_and_demod(True)
             return eng.fetch()
         timing_stream = ts
-    else:
+    elif world == 1:
         def one_step(ptr):
             eng.enqueue_device(ptr)
             return eng.fetch()
