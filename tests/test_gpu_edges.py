@@ -171,3 +171,28 @@ def test_caller_supplied_array_is_copied_into_the_pinned_buffer():
     fb = orc.uploadAndFindCarrier(orc.get_signalBufferHostPointer())
     assert fa[0] == pytest.approx(fb[0], abs=1e-2)
     assert np.array_equal(dem.get_signalBufferHostPointer(), x)
+
+
+def test_concurrent_handles_do_not_interfere():
+    """BASELINE config 5 in miniature: several channels (GMSK and FSK) with one handle / stream / graph each, chunks
+    enqueued on all of them before any result is fetched; every channel must get exactly what it gets alone."""
+    import torch
+    from pycusdr_b200.demodulator import UHF
+    chans = []
+    for c in range(6):
+        mod = "GMSK" if c % 2 == 0 else "FSK"
+        conf = conf_variant(f"benchmark/bench_{mod}.json", blockSize=14, doppCarrierSteps=24)
+        P = protocol_for(conf)
+        sig, _ = S.bench_stream(mod, 12, seed=50 + c)
+        chunks = torch.from_numpy(np.stack([sig[k * 15360:k * 15360 + 16384] for k in range(5, 9)]).astype(np.complex64)).cuda()
+        chans.append((UHF.Demodulator(conf, P, RADIO), UHF.Demodulator(conf, P, RADIO), chunks))
+    for k in range(4):
+        for dem, _, chunks in chans:                       # all channels in flight
+            dem._engine.enqueue_device(chunks[k].data_ptr())
+        got = [tuple(np.copy(a) if isinstance(a, np.ndarray) else a for a in dem._engine.fetch()) for dem, _, _ in chans]
+        for (_, solo, chunks), g in zip(chans, got):        # one at a time
+            solo._engine.enqueue_device(chunks[k].data_ptr())
+            w = solo._engine.fetch()
+            assert g[0].shift == w[0].shift and g[0].n_sym == w[0].n_sym and tuple(g[0].timing) == tuple(w[0].timing)
+            for a, b in zip(g[1:], w[1:]):
+                np.testing.assert_array_equal(a, b)
