@@ -224,6 +224,13 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
 int pcs_stitch_reset(pcs_stitcher* s);
 int pcs_stitch_destroy(pcs_stitcher* s);
 
+/* Decoder-side frame sync search on the bit stream this library hands over (decoder.py:96-104):
+ * score = np.convolve(bits, mask) with mask = protocol.get_mask() (+-1 header, flipped); candidates are the positions
+ * with score >= threshold (= numOnesHeader - headerTol).  idx_out / score_out receive at most `cap` candidates in
+ * increasing order (idx = position in the full convolution; packet start = idx - m + 1); *n_found counts all of them. */
+int pcs_sync_search(const uint8_t* bits, int64_t n, const int8_t* mask, int32_t m, int32_t threshold, int32_t* idx_out,
+                    int32_t* score_out, int32_t cap, int32_t* n_found);
+
 /* Native sample ingest: what the reference's SigFIFO ring buffer (sigFIFO.py:13-181) and the chunk loop of
  * demodulator_process.py:284-338 do on the host, as a pipeline.  Samples are pushed in arbitrary block sizes; every
  * nfft - overlap new samples become a chunk whose first `overlap` samples are carried over from the previous chunk ON

@@ -90,6 +90,7 @@ SYMBOLS = {
     "pcs_ingest_pop": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_ingest_pending": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pcs_ingest_destroy": (C.c_int, [_P]),
+    "pcs_sync_search": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -202,6 +203,29 @@ class Stitcher:
             self.close()
         except Exception:
             pass
+
+
+def sync_search(bits, mask, threshold):
+    """Frame-sync candidates of a demodulated bit stream, exactly as ``decoder.py:96-104`` computes them with
+    ``np.convolve(bits, mask)``: returns ``(idxCand, score[idxCand])`` (int32 arrays)."""
+    lib = load()
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    mask = np.asarray(mask)
+    if mask.size and np.max(np.abs(mask)) > 127:
+        raise ValueError("mask entries must fit int8 (protocol.get_mask() returns +-1)")
+    mask = np.ascontiguousarray(mask, dtype=np.int8)
+    cap = max(16, len(bits) // 8)
+    while True:
+        idx = np.empty(cap, dtype=np.int32)
+        sc = np.empty(cap, dtype=np.int32)
+        n = C.c_int32(0)
+        rc = lib.pcs_sync_search(_ptr(bits), len(bits), _ptr(mask), len(mask), int(threshold), _ptr(idx), _ptr(sc), cap,
+                                 C.byref(n))
+        if rc != 0:
+            raise NativeError(rc, lib.pcs_last_error().decode())
+        if n.value <= cap:
+            return idx[:n.value].copy(), sc[:n.value].copy()
+        cap = n.value
 
 
 class Ingest:

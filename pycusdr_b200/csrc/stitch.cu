@@ -200,4 +200,59 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
     return PCS_OK;
 }
 
+// ---- decoder-side sync search ---------------------------------------------------------------
+// What decoder.py:96-104 does with NumPy on the bit stream the demodulator hands over:
+//   score = np.convolve(bits, mask)            (full convolution, mask = flipud(header * 2 - 1), protocol.get_mask())
+//   idxCand = np.where(score >= numOnesHeader - headerTol)[0];   packetIdx = idxCand - len(mask) + 1
+// Integer arithmetic, so the result is exactly NumPy's.  Returns the candidates (and their scores) in increasing order;
+// *n_found is the total number of candidates even when it exceeds `cap`.
+int pcs_sync_search(const uint8_t* bits, int64_t n, const int8_t* mask, int32_t m, int32_t threshold, int32_t* idx_out,
+                    int32_t* score_out, int32_t cap, int32_t* n_found) {
+    if (!bits || !mask || !n_found || n < 0 || m < 1) return pcs_fail_msg(PCS_ERR_INVALID, "bad argument");
+    // score[i] = sum_j bits[j] * mask[i - j],  0 <= j < n, 0 <= i - j < m,  i in [0, n + m - 1)
+    std::vector<int8_t> rev(mask, mask + m);                 // rev[k] = mask[m - 1 - k]: the header in +-1 form
+    for (int k = 0; k < m / 2; ++k) std::swap(rev[k], rev[m - 1 - k]);
+    int32_t found = 0;
+    const int64_t total = n > 0 ? n + m - 1 : 0;
+    auto emit = [&](int64_t i, int32_t sc) {
+        if (sc >= threshold) {
+            if (found < cap) {
+                if (idx_out) idx_out[found] = (int32_t)i;
+                if (score_out) score_out[found] = sc;
+            }
+            ++found;
+        }
+    };
+    bool pm1 = true, binary = true;
+    for (int k = 0; k < m; ++k) pm1 &= (rev[k] == 1 || rev[k] == -1);
+    for (int64_t j = 0; j < n; ++j) binary &= bits[j] <= 1;
+    if (pm1 && binary) {
+        // +-1 header on a 0/1 stream: score = popcount(window & H) - popcount(window & ~H) on a multi-word shift register
+        // (bit k of the register = window sample k, the newest sample enters at bit m - 1)
+        const int W = (m + 63) / 64;
+        std::vector<uint64_t> H(W, 0), nH(W, 0), reg(W, 0);
+        for (int k = 0; k < m; ++k) (rev[k] > 0 ? H : nH)[k >> 6] |= 1ull << (k & 63);
+        const int top = (m - 1) >> 6, topbit = (m - 1) & 63;
+        for (int64_t i = 0; i < total; ++i) {
+            for (int w = 0; w < W - 1; ++w) reg[w] = (reg[w] >> 1) | (reg[w + 1] << 63);
+            reg[W - 1] >>= 1;
+            if (i < n && bits[i]) reg[top] |= 1ull << topbit;
+            int32_t sc = 0;
+            for (int w = 0; w < W; ++w) sc += __builtin_popcountll(reg[w] & H[w]) - __builtin_popcountll(reg[w] & nH[w]);
+            emit(i, sc);
+        }
+    } else {
+        std::vector<uint8_t> pad((size_t)n + 2 * (size_t)(m - 1), 0);
+        if (n > 0) memcpy(pad.data() + (m - 1), bits, (size_t)n);
+        for (int64_t i = 0; i < total; ++i) {
+            const uint8_t* w = pad.data() + i;                   // window bits[i - m + 1 .. i], zero padded
+            int32_t sc = 0;
+            for (int k = 0; k < m; ++k) sc += (int32_t)w[k] * (int32_t)rev[k];
+            emit(i, sc);
+        }
+    }
+    *n_found = found;
+    return PCS_OK;
+}
+
 }  // extern "C"

@@ -76,3 +76,33 @@ def test_native_stitcher_errors_mirror_the_reference():
     with pytest.raises(NotImplementedError):
         _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
                          bit_lut=None, symbol_lut=np.zeros((4, 3)))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_sync_search_equals_numpy_convolve(seed):
+    """decoder.py:96-104 on the handed-over bit stream: native integer search vs np.convolve."""
+    import time
+    rng = np.random.RandomState(seed)
+    header = rng.randint(0, 2, 128)
+    mask = np.flipud(header * 2 - 1)                      # protocol.get_mask() of the benchmark protocols
+    bits = rng.randint(0, 2, 20000).astype(np.uint8)
+    for pos in (0, 777, 9000, 20000 - 128):               # plant headers with a few bit errors
+        h = header.copy()
+        h[rng.choice(128, size=rng.randint(0, 20), replace=False)] ^= 1
+        bits[pos:pos + 128] = h
+    thr = int(np.sum(header)) - 27                        # numOnesHeader - headerTol (bench_base.py:62-64)
+    t0 = time.perf_counter()
+    score = np.convolve(bits.astype(np.float64), mask)
+    want = np.where(score >= thr)[0]
+    t_np = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    idx, sc = _native.sync_search(bits, mask, thr)
+    t_nat = time.perf_counter() - t0
+    np.testing.assert_array_equal(idx, want)
+    np.testing.assert_array_equal(sc, score[want].astype(np.int32))
+    assert set((want - 127).tolist()) >= {0, 777, 9000, 20000 - 128}
+    assert len(_native.sync_search(np.zeros(0, np.uint8), mask, thr)[0]) == 0
+    # every candidate when the threshold is low enough to overflow the first output buffer
+    idx2, _ = _native.sync_search(bits, mask, -10)
+    np.testing.assert_array_equal(idx2, np.where(score >= -10)[0])
+    print(f"np.convolve {t_np * 1e3:.2f} ms, native {t_nat * 1e3:.2f} ms")
