@@ -377,6 +377,9 @@ def main():
     ap.add_argument("--log2-block", type=int, default=0)
     ap.add_argument("--groups-per-cta", type=int, default=0, help="tuning knob of the 256-point search kernel")
     ap.add_argument("--xb-smem", action="store_true", help="tuning knob: block spectrum in shared memory")
+    ap.add_argument("--search-form", type=int, default=0,
+                    help="256-point search: 0 shifted filters (default), 1 / 2 rotate-the-chunk comparison variants")
+    ap.add_argument("--items-per-cta", type=int, default=0, help="tuning knob of the shifted-filter search kernel")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=0,
@@ -421,7 +424,9 @@ def main():
     dev_chunks = torch.from_numpy(host_chunks).cuda()
     ring_bytes = dev_chunks.numel() * 8
 
-    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem)
+    knobs = dict(groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem, search_form=args.search_form,
+                 items_per_cta=args.items_per_cta)
+    dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, **knobs)
     eng = dem._engine
     D, M = eng.D, eng.M
     plan = eng.plan()
@@ -437,8 +442,7 @@ def main():
             dist.all_gather_object(out, obj)
             return out
         K = max(1, args.inflight)
-        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta,
-                                 xb_smem=args.xb_smem) for _ in range(K - 1)]
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, **knobs) for _ in range(K - 1)]
         engs = [eng] + [d._engine for d in extra]
         p2p_error = None
         try:
@@ -452,8 +456,7 @@ def main():
                 print(f"bench: peer-memory exchange unavailable ({p2p_error}); using the NCCL all-gather path", file=sys.stderr)
             sh = None
             args.exchange = "nccl"
-            dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta,
-                                  xb_smem=args.xb_smem)
+            dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, **knobs)
             eng = dem._engine
         else:
             lo, hi = sh.slices[rank]
@@ -495,7 +498,7 @@ def main():
         # chunks in flight: handle k % K takes chunk k, so the latency-bound tail of one chunk (estimate, demod, timing,
         # symbol decisions, result copies) overlaps the search kernel of the next one
         K = max(1, args.inflight)
-        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem)
+        extra = [UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, **knobs)
                  for _ in range(K - 1)]
         engs = [eng] + [d._engine for d in extra]
         streams = [torch.cuda.ExternalStream(e.stream) for e in engs]

@@ -58,8 +58,11 @@ typedef struct {
     int32_t path;                    /* pcs_path */
     int32_t log2_block;              /* 0 = choose; else force the overlap-save block size 2**log2_block */
     int32_t snr_window;              /* half width of the computeSNR windows (5)    dem_base:620 */
-    int32_t reserved[3];             /* [0] bit 0: 1 = never replay the per-chunk sequence as a CUDA graph; [1] groups per CTA of
-                                        the 256-point search kernel (0 = default = 8, or 16); [2] must be 0 */
+    int32_t reserved[3];             /* tuning knobs, all 0 by default.  [0] bit 0: 1 = never replay the per-chunk sequence as a
+                                        CUDA graph; [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
+                                        8+: (bin, block) items per CTA of the shifted-filter search kernel (0 = 64); [2] form of the
+                                        256-point search: 0 = shifted filters (block spectra shared by all bins), 1 / 2 = rotate the
+                                        chunk per bin with the block spectrum in shared memory / registers (comparison variants) */
 } pcs_config;
 
 /* Per-chunk scalar results (filled by pcs_search / pcs_demod / pcs_process). */
@@ -223,6 +226,25 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
                      uint8_t* trust_out, int32_t* n_out);
 int pcs_stitch_reset(pcs_stitcher* s);
 int pcs_stitch_destroy(pcs_stitcher* s);
+
+/* computeSNR's two window means (dem_base:657-663): mean |X| over the signal and the noise window gathered by the last
+ * search, when the windows do not touch the ends of the spectrum (*ok = 1); otherwise *ok = 0 and the caller applies the
+ * reference's slicing rules to pcs_snr_windows / pcs_get_spectrum itself.  shifts = the table given to pcs_create. */
+int pcs_snr_means(pcs_handle* h, const int32_t* shifts, float* sig_mean, float* noise_mean, int32_t* ok);
+
+/* mean(|z|) of complex64[n] as float32 (np.mean(np.abs(z)) of dem_base:657-661; host only, no GPU): the one
+ * implementation every schedule uses for the two computeSNR window means. */
+int pcs_mean_abs_c64(const float* z, int32_t n, float* out);
+
+/* Whole chunk in one call for a host that wants bits (UHF backend): pcs_upload + pcs_process + pcs_snr_means +
+ * pcs_stitch_chunk; the symbol tables go from the result staging area to the stitcher inside the library.  E_out, sym,
+ * centre, mag (inspection copies) and the three SNR outputs may be NULL.  When the device part succeeded and only the
+ * stitcher failed (the reference raises from demodulate() in that case, dem_base:868-869), the stitcher's status is
+ * returned with *n_out = -1 and res / E_out / sym / centre / mag are valid. */
+int pcs_chunk_to_bits(pcs_handle* h, pcs_stitcher* st, const int32_t* shifts, const int64_t* clipped, int32_t n_clipped,
+                      pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag, float* sig_mean,
+                      float* noise_mean, int32_t* snr_ok, uint8_t* bits_out, uint8_t* centres_out, uint8_t* trust_out,
+                      int32_t* n_out);
 
 /* Decoder-side frame sync search on the bit stream this library hands over (decoder.py:96-104):
  * score = np.convolve(bits, mask) with mask = protocol.get_mask() (+-1 header, flipped); candidates are the positions

@@ -90,6 +90,10 @@ SYMBOLS = {
     "pcs_ingest_pop": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_ingest_pending": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pcs_ingest_destroy": (C.c_int, [_P]),
+    "pcs_snr_means": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "pcs_mean_abs_c64": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
+    "pcs_chunk_to_bits": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, C.POINTER(C.c_float),
+                                    C.POINTER(C.c_float), C.POINTER(C.c_int32), _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_sync_search": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
@@ -141,6 +145,16 @@ def measure_fp32_peak(device=0):
     if rc != 0:
         raise NativeError(rc, lib.pcs_last_error().decode())
     return out.value
+
+
+def mean_abs_c64(z):
+    """float32 mean of |z| for a complex64 window (``pcs_mean_abs_c64``; host only)."""
+    z = np.ascontiguousarray(z, dtype=np.complex64)
+    out = C.c_float(0)
+    rc = load().pcs_mean_abs_c64(z.__array_interface__["data"][0], len(z), C.byref(out))
+    if rc != 0:
+        raise NativeError(rc, load().pcs_last_error().decode())
+    return np.float32(out.value)
 
 
 def _ptr(a):
@@ -296,7 +310,8 @@ class Engine:
     """Thin object wrapper over one ``pcs_handle`` (one CUDA stream, one pinned chunk buffer)."""
 
     def __init__(self, *, device, nfft, num_dopplers, element_offset, shifts, masks, window_width, sum_all_masks,
-                 code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5, use_graph=True, groups_per_cta=0, xb_smem=False):
+                 code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5, use_graph=True, groups_per_cta=0, xb_smem=False,
+                 search_form=0, items_per_cta=0):
         self.lib = load()
         shifts = np.ascontiguousarray(shifts, dtype=np.int32)
         masks = np.ascontiguousarray(masks, dtype=np.complex64)
@@ -307,8 +322,9 @@ class Engine:
         cfg = Config(ABI_VERSION, device, nfft, num_dopplers, element_offset, masks.shape[0], window_width,
                      int(bool(sum_all_masks)), code_search_mask_offset, samples_per_sym, path, log2_block, snr_window)
         cfg.reserved[0] = 0 if use_graph else 1      # bit 0: do not capture the per-chunk sequence in a CUDA graph
-        cfg.reserved[1] = int(groups_per_cta)        # tuning knob of the 256-point search kernel (0 = default)
-        cfg.reserved[2] = int(bool(xb_smem))         # tuning knob: block spectrum in shared memory instead of registers
+        cfg.reserved[1] = int(groups_per_cta) | (int(items_per_cta) << 8)    # tuning knobs of the 256-point search kernels
+        # form of the 256-point search: 0 shifted filters (default), 1 rotate + block spectrum in shared memory, 2 rotate
+        cfg.reserved[2] = 1 if xb_smem else int(search_form)
         self._h = _P()
         self.nfft, self.D, self.M = nfft, num_dopplers + element_offset, masks.shape[0]
         self._check(self.lib.pcs_create(C.byref(cfg), _ptr(shifts), _ptr(masks), C.byref(self._h)))
@@ -373,6 +389,37 @@ class Engine:
                                        _ptr(self._mag)))
         n = res.n_sym
         return res, self._E, self._sym[:n], self._centre[:n], self._mag[:n]
+
+    def snr_means(self, shifts):
+        """(mean |X| signal window, mean |X| noise window) or None when the window geometry needs the general path."""
+        a, b, ok = C.c_float(0), C.c_float(0), C.c_int32(0)
+        self._check(self.lib.pcs_snr_means(self._h, _ptr(shifts), C.byref(a), C.byref(b), C.byref(ok)))
+        return (np.float32(a.value), np.float32(b.value)) if ok.value else None
+
+    def chunk_to_bits(self, stitcher, shifts, clipped):
+        """upload + search + demod + SNR means + bit post-processing of the chunk in the pinned buffer, one native call.
+        Returns (res, E, sym, centre, mag, snr_means or None, bits, centres, trust)."""
+        n = self.max_sym
+        if getattr(self, "_bits", None) is None:
+            self._bits, self._cen8, self._tr8 = (np.empty(n, dtype=np.uint8) for _ in range(3))
+        clipped = np.ascontiguousarray(clipped, dtype=np.int64)
+        res, a, b, ok, n_out = Result(), C.c_float(0), C.c_float(0), C.c_int32(0), C.c_int32(0)
+        rc = self.lib.pcs_chunk_to_bits(self._h, stitcher._h, _ptr(shifts), _ptr(clipped), len(clipped), C.byref(res),
+                                        _ptr(self._E), _ptr(self._sym), _ptr(self._centre), _ptr(self._mag), C.byref(a),
+                                        C.byref(b), C.byref(ok), _ptr(self._bits), _ptr(self._cen8), _ptr(self._tr8),
+                                        C.byref(n_out))
+        err = None
+        if rc != 0 and n_out.value == -1:
+            # the device part succeeded and the stitcher refused the symbol table (IndexError = what the reference's
+            # np.where(...)[0][0] raises from demodulate()); handed back so that the caller can raise it there
+            msg = self.lib.pcs_last_error().decode()
+            err = IndexError(msg) if rc == -4 else NativeError(rc, msg)
+        else:
+            self._check(rc)
+        k, ns = max(n_out.value, 0), res.n_sym
+        means = (np.float32(a.value), np.float32(b.value)) if ok.value else None
+        return (res, self._E, self._sym[:ns], self._centre[:ns], self._mag[:ns], means,
+                self._bits[:k].copy(), self._cen8[:k].copy(), self._tr8[:k].copy(), err)
 
     def snr_windows(self, res):
         sig = np.empty(max(res.sig_len, 0), dtype=np.complex64)

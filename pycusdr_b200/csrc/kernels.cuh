@@ -345,6 +345,169 @@ __global__ void __launch_bounds__(G * 16, XBS ? 40 / G : 32 / G) search_os256_ke
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a6 + a7 + a8 fused, "shifted filter" form of the 256-point search (default for M <= 16).
+// The reference's spectrum shift can be charged to the filter instead of the chunk:
+//   y[d,m,n] = sum_k X[(k+s_d)%N] Mk[m,k] e^{+2 pi i k n/N} = e^{-2 pi i s_d n/N} * sum_k X[k] Mk[m,(k-s_d)%N] e^{+2 pi i k n/N},
+// and the unit-modulus factor drops out of |y|^2 (kern:339-373 + kern:421-480 only ever use |y|^2).  So the block
+// spectra of the *unrotated* chunk are computed once per chunk (block_spectra256_kernel: nblk forward transforms instead
+// of D * nblk) and every Doppler bin gets its own set of 256-point filter spectra G[d][m][k] = Mk[m][(k N/256 - s_d) % N] N/256,
+// a pure gather from the protocol's own spectra done once per handle (shifted_filters256_kernel).  One item = one
+// (bin, block): load 2 KB of block spectrum, then M x (filter product + inverse transform + |y|^2 sum / max).
+// A CTA works on items_per_cta consecutive items of the (bin-major) item space; the bin's filter spectra sit in shared
+// memory and are reloaded when the CTA crosses into the next bin.
+// ---------------------------------------------------------------------------------------------
+struct Fs256Params {
+    const float4* __restrict__ xbs;     // [nblk][8][16] float4: block spectra, lane-major pairs (X[t+32rr], X[t+32rr+16])
+    const float4* __restrict__ gs;      // [D][M][8][16] float4: Doppler-shifted filter spectra (x N/256), same layout
+    const float2* __restrict__ tw;      // [256] exp(-2 pi i t / 256)
+    float* __restrict__ psum;           // [nblk][D][M]
+    float* __restrict__ pmax;           // [nblk][D][M]
+    int N, D, M, nblk, V, Lpos, items_per_cta;
+};
+
+// Block spectra of the chunk: block b = FFT_256(x[(b V - Lpos + i) % N], i = 0..255), one 16-lane group per block.
+__global__ void __launch_bounds__(256) block_spectra256_kernel(const float2* __restrict__ x, const float2* __restrict__ twg,
+                                                               float4* __restrict__ xbs, int N, int nblk, int V, int Lpos) {
+    __shared__ float2 sbuf[16][272];
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    float2 tw[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) tw[r] = __ldg(&twg[(t * r) & 255]);
+    tw[0] = make_float2(1.f, 0.f);
+    int blk = blockIdx.x * 16 + g;
+    const bool live = blk < nblk;
+    if (!live) blk = nblk - 1;
+    const uint32_t nmask = (uint32_t)N - 1u, n_first = (uint32_t)(blk * V - Lpos) & nmask;
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = __ldg(&x[(n_first + (uint32_t)(t + 16 * r)) & nmask]);
+    fft256_regs<-1>(v, sbuf[g], tw, t);
+    if (live) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const float2 a = v[dft_q<16>(2 * rr)], b = v[dft_q<16>(2 * rr + 1)];     // natural order X[t + 16 r]
+            xbs[(size_t)blk * 128 + rr * 16 + t] = make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
+}
+
+// G[d][m][k] = Mk[m][(k N/256 - s_d) % N] * N/256 in the lane-major pair layout (once per handle).
+__global__ void shifted_filters256_kernel(const float2* __restrict__ masks, const int* __restrict__ shifts,
+                                          float4* __restrict__ gs, int N, int D, int M) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D * M * 128) return;
+    const int t = (int)(idx & 15), rr = (int)((idx >> 4) & 7);
+    const int dm = (int)(idx >> 7), m = dm % M, d = dm / M;
+    const uint32_t nmask = (uint32_t)N - 1u, dec = (uint32_t)(N >> 8), s = (uint32_t)shifts[d];
+    const float scale = (float)dec;
+    const float2 a = masks[(size_t)m * N + (((uint32_t)(t + 32 * rr) * dec - s) & nmask)];
+    const float2 b = masks[(size_t)m * N + (((uint32_t)(t + 32 * rr + 16) * dec - s) & nmask)];
+    gs[idx] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+}
+
+// v = IFFT_256(xb * g) with g read as float4 pairs at stride 16 from g4 (shared or global memory, already offset by t).
+PCS_DEVINL void fs256_filter(const float4* g4, const float2* xb, float2* buf, const float2* tw, int t, float2* v) {
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const float4 g = g4[rr * 16];
+        v[2 * rr] = cmul(xb[2 * rr], make_float2(g.x, g.y));
+        v[2 * rr + 1] = cmul(xb[2 * rr + 1], make_float2(g.z, g.w));
+    }
+    fft256_regs<+1>(v, buf, tw, t);
+}
+
+PCS_DEVINL unsigned fs256_valid_mask(int Lpos, int vlen, int t) {
+    unsigned vm = 0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int rel = t + 16 * dft_q<16>(s) - Lpos;
+        if (rel >= 0 && rel < vlen) vm |= 1u << s;
+    }
+    return vm;
+}
+
+template <int G>     // G = groups (half warps) per CTA
+__global__ void __launch_bounds__(G * 16, 32 / G) search_fs256_kernel(Fs256Params p) {
+    __shared__ float2 sbuf[G][272];
+    extern __shared__ float4 s_dyn[];         // [M][128] float4 filter spectra of the current bin | [G][2][M][17] float partials
+    float4* s_g = s_dyn;
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    float2* buf = sbuf[g];
+    float* acc_sum = reinterpret_cast<float*>(s_dyn + (size_t)p.M * 128) + (size_t)g * 2 * p.M * 17;
+    float* acc_max = acc_sum + (size_t)p.M * 17;
+    float2 tw[16];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) tw[r] = __ldg(&p.tw[(t * r) & 255]);
+    tw[0] = make_float2(1.f, 0.f);
+    const unsigned vm_full = fs256_valid_mask(p.Lpos, p.V, t);
+    const long long total = (long long)p.nblk * p.D;
+    long long cur = (long long)blockIdx.x * p.items_per_cta;
+    const long long end = min(cur + (long long)p.items_per_cta, total);
+    while (cur < end) {
+        const int d = (int)(cur / p.nblk);
+        const int b0 = (int)(cur - (long long)d * p.nblk);
+        const int nb = (int)min((long long)(p.nblk - b0), end - cur);
+        __syncthreads();                      // everyone is done with the previous bin's spectra
+        {
+            const float4* __restrict__ src = p.gs + (size_t)d * p.M * 128;
+            for (int i = threadIdx.x; i < p.M * 128; i += G * 16) s_g[i] = __ldg(&src[i]);
+        }
+        __syncthreads();
+        const int iters = (nb + G - 1) / G;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            int b = it * G + g;
+            const bool live = b < nb;
+            if (!live) b = nb - 1;            // keep both halves of the warp convergent; the duplicate's results are dropped
+            const int blk = b0 + b;
+            const int vlen = min(p.V, p.N - blk * p.V);
+            const unsigned vm = vlen == p.V ? vm_full : fs256_valid_mask(p.Lpos, vlen, t);
+            float2 xb[16];
+            {
+                const float4* __restrict__ xs = p.xbs + (size_t)blk * 128 + t;
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const float4 q = __ldg(&xs[rr * 16]);
+                    xb[2 * rr] = make_float2(q.x, q.y);
+                    xb[2 * rr + 1] = make_float2(q.z, q.w);
+                }
+            }
+#pragma unroll 1
+            for (int m = 0; m < p.M; ++m) {
+                float2 v[16];
+                fs256_filter(s_g + (size_t)m * 128 + t, xb, buf, tw, t, v);
+                float sum = 0.f, best = 0.f;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const float mag = (vm >> s) & 1u ? cabs2(v[s]) : 0.f;
+                    sum += mag;
+                    best = fmaxf(best, mag);
+                }
+                acc_sum[m * 17 + t] = sum;    // per-lane partials parked in shared memory: no cross-lane traffic in the loop
+                acc_max[m * 17 + t] = best;
+            }
+            __syncwarp();
+            // lane m folds the 16 lanes of mask m in lane order (fixed order -> bit-reproducible) and stores the pair
+            for (int m = t; m < p.M; m += 16) {
+                float sum = 0.f, best = 0.f;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                    sum += acc_sum[m * 17 + l];
+                    best = fmaxf(best, acc_max[m * 17 + l]);
+                }
+                if (live) {
+                    const size_t o = ((size_t)blk * p.D + d) * p.M + m;
+                    p.psum[o] = sum;
+                    p.pmax[o] = best;
+                }
+            }
+            __syncwarp();                     // the fold has read the partials before the next item overwrites them
+        }
+        cur += nb;
+    }
+}
+
 // Column reduction of the [nblk][DM] partials in a fixed order, stage 1: slice z of PCS_RED_SLICES takes blocks
 // z, z + S, z + 2S, ... and warp w of the CTA every 32nd of those; partial (sum, max, first block) per slice.
 #define PCS_RED_SLICES 8
@@ -407,7 +570,8 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
                                                                 float* __restrict__ Efull, float* __restrict__ peak_val,
                                                                 int* __restrict__ peak_off, unsigned int* done_counter,
                                                                 unsigned long long* arrival_flag,
-                                                                unsigned long long arrival_value) {
+                                                                unsigned long long arrival_value,
+                                                                const float4* __restrict__ xbs, const float4* __restrict__ gs) {
     __shared__ float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
@@ -439,8 +603,18 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
     }
     const Os256Item it = os256_item(p, (long long)wblk * p.D + d);
     float2 xb[16], v[16];
-    os256_block_spectrum(p, it, buf, tw, t, xb);
-    os256_filter(p, m, xb, buf, tw, t, v);
+    if (xbs != nullptr) {      // shifted-filter form: the very products the search kernel evaluated
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const float4 q = __ldg(&xbs[(size_t)wblk * 128 + rr * 16 + t]);
+            xb[2 * rr] = make_float2(q.x, q.y);
+            xb[2 * rr + 1] = make_float2(q.z, q.w);
+        }
+        fs256_filter(gs + (size_t)col * 128 + t, xb, buf, tw, t, v);
+    } else {
+        os256_block_spectrum(p, it, buf, tw, t, xb);
+        os256_filter(p, m, xb, buf, tw, t, v);
+    }
     float best = -1.f;
     int idx = 0x7fffffff;
 #pragma unroll

@@ -86,6 +86,9 @@ struct pcs_handle {
     bool fast256 = false;
     int nblk256 = 0, V256 = 0;
     float4* d_gperm = nullptr;
+    bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
+    float4 *d_xbs = nullptr, *d_gs = nullptr;
+    int fs_items = 64;                 // items (bin, block) per CTA
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
     int* d_part_blk = nullptr;
     float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
@@ -424,6 +427,21 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_done, (size_t)1)) return rc;
     CUDA_TRY(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
     h->fast256 = true;
+    // Shifted-filter form (default): per-bin filter spectra gathered once from the protocol's spectra, block spectra of
+    // the unrotated chunk once per chunk.  reserved[2]: 0 = this form, 1 / 2 = rotate-the-chunk kernel (block spectrum
+    // in shared memory / registers), kept as comparison variants.  More than 16 masks keep the rotate kernel (the
+    // bin's spectra would not leave room for four CTAs per SM).
+    if (h->cfg.reserved[2] == 0 && M <= 16) {
+        if (int rc = dev_alloc(h, &h->d_xbs, (size_t)h->nblk256 * 128)) return rc;
+        if (int rc = dev_alloc(h, &h->d_gs, (size_t)D * M * 128)) return rc;
+        const long long n = (long long)D * M * 128;
+        shifted_filters256_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_masks, h->d_shifts, h->d_gs, N, D, M);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        const int ipc = h->cfg.reserved[1] >> 8;
+        h->fs_items = ipc > 0 ? ipc : 64;
+        h->fs256 = true;
+    }
     return 0;
 }
 
@@ -644,9 +662,11 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
     info->num_blocks = h->fast256 ? h->nblk256 : h->nblk;
     info->support_pos = h->Lpos;
     info->support_neg = h->Lneg;
-    info->groups_per_cta = h->fast256 ? (h->cfg.reserved[1] == 16 ? 16 : 8) : h->G;
-    info->search_ctas = h->fast256 ? (int)(((long long)h->nblk256 * h->D + 15) / 16)
-                                   : (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
+    const int gk = h->cfg.reserved[1] & 0xff, g256 = gk == 16 ? 16 : gk == 4 ? 4 : 8;
+    info->groups_per_cta = h->fast256 ? g256 : h->G;
+    info->search_ctas = h->fs256 ? (int)(((long long)h->nblk256 * h->D + h->fs_items - 1) / h->fs_items)
+                        : h->fast256 ? (int)(((long long)h->nblk256 * h->D + g256 - 1) / g256)
+                                     : (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
     info->search_smem_bytes = h->search_smem;
     info->sm_count = h->sm_count;
     info->device_bytes = h->dev_bytes;
@@ -677,10 +697,34 @@ static int enqueue_search_local256(pcs_handle* h) {
     const float2* twp = nullptr;
     if (int rc = get_twiddles(h, 8, &twp)) return rc;
     p.tw = twp;
-    {
+    const int Gk = h->cfg.reserved[1] & 0xff;
+    if (h->fs256) {
+        StageTimer t(h, PCS_STAGE_SEARCH);
+        block_spectra256_kernel<<<(p.nblk + 15) / 16, 256, 0, h->stream>>>(p.x, p.tw, h->d_xbs, p.N, p.nblk, p.V, p.Lpos);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        Fs256Params q{};
+        q.xbs = h->d_xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = p.psum; q.pmax = p.pmax;
+        q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos; q.items_per_cta = h->fs_items;
+        const long long items = (long long)p.nblk * Dl;
+        const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
+        h->search_ctas = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
+        const size_t dyn = (size_t)p.M * 128 * sizeof(float4) + (size_t)G * 2 * p.M * 17 * sizeof(float);
+        h->search_smem = (int)(G * 272 * sizeof(float2) + dyn);
+        static size_t configured[PCS_MAX_DEVICES][3] = {};
+        const int gi = G == 16 ? 0 : G == 8 ? 1 : 2;
+        auto kern = G == 16 ? search_fs256_kernel<16> : G == 8 ? search_fs256_kernel<8> : search_fs256_kernel<4>;
+        if (configured[h->cfg.device][gi] < dyn) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured[h->cfg.device][gi] = dyn;
+        }
+        kern<<<h->search_ctas, G * 16, dyn, h->stream>>>(q);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
         StageTimer t(h, PCS_STAGE_SEARCH);
         const long long items = (long long)p.nblk * Dl;
-        const int G = h->cfg.reserved[1] == 16 ? 16 : h->cfg.reserved[1] == 4 ? 4 : 8;   // groups per CTA (8: measured best)
+        const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;   // groups per CTA (8: measured best)
         h->search_ctas = (int)((items + G - 1) / G);
         const size_t acc_bytes = (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + acc_bytes);
@@ -705,7 +749,9 @@ static int enqueue_search_local256(pcs_handle* h) {
     CUDA_TRY(cudaGetLastError());
     peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_part_sum, h->d_part_max, h->d_part_blk,
                                                                   h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0,
-                                                                  h->d_done, h->push_flag, h->push_value);
+                                                                  h->d_done, h->push_flag, h->push_value,
+                                                                  h->fs256 ? h->d_xbs : nullptr,
+                                                                  h->fs256 ? h->d_gs + (size_t)h->bin_lo * h->M * 128 : nullptr);
     h->push_flag = nullptr;       // consumed: the locate kernel raises the flag itself
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1108,6 +1154,62 @@ int pcs_snr_windows(pcs_handle* h, float* sig_win, float* noise_win) {
     if (sig_win) memcpy(sig_win, h->h_sigwin, sizeof(float2) * std::max(h->h_res->sig_len, 0));
     if (noise_win) memcpy(noise_win, h->h_noisewin, sizeof(float2) * std::max(h->h_res->noise_len, 0));
     return PCS_OK;
+}
+
+// mean(|z|) of a complex64 window as float32: magnitudes by hypotf, accumulated in double, rounded once.  (NumPy's own
+// np.abs / np.mean differ from this in the last ulp depending on the host's SIMD dispatch; every schedule of this
+// library -- two-step, fused, one-call, streaming -- goes through this one function, so they agree exactly.)
+static float mean_abs(const float2* z, int n) {
+    double a = 0;
+    for (int i = 0; i < n; ++i) a += (double)hypotf(z[i].x, z[i].y);
+    return (float)(a / n);
+}
+
+// computeSNR's two window means (dem_base:657-663) for the common geometry in which neither window touches the ends
+// of the spectrum, so that the reference's slices X[a-w : b+w] are exactly the gathered windows.  *ok = 0 otherwise
+// (the caller then evaluates the reference's slicing rules itself).
+int pcs_snr_means(pcs_handle* h, const int32_t* shifts, float* sig_mean, float* noise_mean, int32_t* ok) {
+    if (!h || !shifts || !sig_mean || !noise_mean || !ok) return fail(PCS_ERR_INVALID, "null argument");
+    if (!h->searched) return fail(PCS_ERR_STATE, "pcs_snr_means before a search");
+    const pcs_result* r = reinterpret_cast<const pcs_result*>(h->h_res);
+    *ok = 0;
+    if (r->status != 0 || r->sig_len <= 0) return PCS_OK;
+    const int N = h->N, w = h->cfg.snr_window;
+    const int lo = shifts[r->low_idx], hi = shifts[r->high_idx];
+    const int nlo = (lo + N / 2) % N, nhi = (hi + N / 2) % N;
+    if (!(lo <= hi && nlo <= nhi && lo - w >= 0 && nlo - w >= 0 && hi + w <= N && nhi + w <= N && r->sig_start == lo - w &&
+          r->noise_start == nlo - w && r->sig_len == hi - lo + 2 * w && r->noise_len == nhi - nlo + 2 * w))
+        return PCS_OK;
+    *sig_mean = mean_abs(h->h_sigwin, r->sig_len);
+    *noise_mean = mean_abs(h->h_noisewin, r->noise_len);
+    *ok = 1;
+    return PCS_OK;
+}
+
+int pcs_mean_abs_c64(const float* z, int32_t n, float* out) {
+    if (!z || !out || n < 1) return fail(PCS_ERR_INVALID, "pcs_mean_abs_c64: bad argument");
+    *out = mean_abs(reinterpret_cast<const float2*>(z), n);
+    return PCS_OK;
+}
+
+// One call per chunk for a host that wants bits: pcs_upload + pcs_process + pcs_snr_means + pcs_stitch_chunk, with the
+// symbol tables handed from the result staging area to the stitcher without leaving the library.  sym / centre / mag
+// (inspection copies) and E_out may be NULL.
+int pcs_chunk_to_bits(pcs_handle* h, pcs_stitcher* st, const int32_t* shifts, const int64_t* clipped, int32_t n_clipped,
+                      pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag, float* sig_mean,
+                      float* noise_mean, int32_t* snr_ok, uint8_t* bits_out, uint8_t* centres_out, uint8_t* trust_out,
+                      int32_t* n_out) {
+    if (!h || !st || !res || !n_out) return fail(PCS_ERR_INVALID, "null argument");
+    if (int rc = pcs_upload(h)) return rc;
+    if (int rc = pcs_process(h, res, E_out, sym, centre, mag)) return rc;
+    *n_out = 0;
+    if (snr_ok) {
+        if (int rc = pcs_snr_means(h, shifts, sig_mean, noise_mean, snr_ok)) return rc;
+    }
+    const int n = std::min(std::max(h->h_res->n_sym, 0), h->max_sym);
+    *n_out = -1;      // from here on a failure is the stitcher's: res, E and the symbol tables are valid
+    return pcs_stitch_chunk(st, h->h_sym, h->h_centre, h->h_mag, n, clipped, n_clipped, h->h_res->sp_sym, bits_out, centres_out,
+                            trust_out, n_out);
 }
 
 int pcs_get_spectrum(pcs_handle* h, float* X_out) {

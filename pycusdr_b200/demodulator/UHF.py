@@ -6,6 +6,8 @@ from .demodulator_base import Demodulator as Demodulator_base
 class Demodulator(Demodulator_base):
 
     def uploadAndFindCarrier(self, samples):
+        if self.fused and self.one_call and self._stitch is not None:
+            return self.chunkToBits(samples)      # same results, one native call for the whole chunk
         self.uploadToGPU(samples)
         return self.findUHF(samples)
 

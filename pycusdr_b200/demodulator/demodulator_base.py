@@ -8,8 +8,10 @@ peak tagging (:817-837), the STX input thresholding (:670-707) and the output ca
 
 Differences from the reference that a caller can observe (DESIGN.md "quirks"):
   * search and demodulation of a chunk are enqueued together in ``uploadAndFindCarrier`` (one
-    synchronisation per chunk instead of five); ``demodulate`` then only post-processes.  Set
-    ``fused=False`` to get the reference's two-step device schedule.
+    synchronisation per chunk instead of five), and with the native bit post-processing the whole
+    chunk is ONE native call (``pcs_chunk_to_bits``); ``demodulate`` then only hands the bits over.
+    ``one_call=False`` keeps the post-processing in ``demodulate``; ``fused=False`` gives the
+    reference's two-step device schedule.  All three produce identical outputs.
   * ``E`` is reduced in a fixed order, so results are bit-reproducible run to run (the reference's
     float atomics are not, kern:463,474).
   * there is no ``extractBitsOld`` (undefined in the reference too, dem_base:1017).
@@ -36,12 +38,13 @@ SNR_WINDOW = 5              # dem_base:620
 class Demodulator:
 
     def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True,
-                 native_post=True, groups_per_cta=0, xb_smem=False):
+                 native_post=True, groups_per_cta=0, xb_smem=False, search_form=0, items_per_cta=0, one_call=True):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
         self.confGPU = confGPU = conf["GPU"][confRadio["CUDA_settings"]]
         self.fused = fused
+        self.one_call = one_call
 
         # chunk geometry (dem_base:89-93)
         self.sigLen = 2 ** confGPU["blockSize"]
@@ -123,7 +126,8 @@ class Demodulator:
             element_offset=self.doppIdxArrayOffset, shifts=self.doppCyperSymNorm, masks=masks,
             window_width=self.windowWidth, sum_all_masks=self.SUM_ALL_MASKS_PYTHON,
             code_search_mask_offset=self.CODE_SEARCH_MASK_OFFSET, samples_per_sym=self.spsym, path=path,
-            log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph, groups_per_cta=groups_per_cta, xb_smem=xb_smem)
+            log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph, groups_per_cta=groups_per_cta, xb_smem=xb_smem,
+            search_form=search_form, items_per_cta=items_per_cta)
         self._engine = _native.Engine(**self._engine_kwargs)
         self.GPU_bufSignalTime_cpu_handle = self._engine.host_buffer
         # bit extraction + chunk stitching + trust tagging in one native call (the NumPy methods below stay as the
@@ -142,6 +146,7 @@ class Demodulator:
         self.posSymEnd = None
         self.dopplerIdxlast = 0
         self._pending = None        # device results of the chunk currently being processed
+        self._bits_ready = None     # ... and its finished bits when the whole chunk ran in one native call
         self.last = {}              # inspection: raw per-chunk device outputs
         log.info("[{}]: Initialization done ({})".format(radioName, self._engine.plan()))
 
@@ -169,6 +174,7 @@ class Demodulator:
         self._as_chunk_buffer(samples)
         self._engine.upload()
         self._pending = None
+        self._bits_ready = None
 
     def thresholdInput(self, samples):
         self.__thresholdInput(samples)
@@ -178,6 +184,17 @@ class Demodulator:
         self.__thresholdInput(samples)
         self.uploadToGPU(samples)
         return self.findUHF(samples)
+
+    def chunkToBits(self, samples):
+        """uploadToGPU + findUHF + the whole of demodulate() in ONE native call (``pcs_chunk_to_bits``): the fused
+        schedule with the symbol tables handed to the stitcher inside the library.  Returns what findUHF returns; the
+        bits are parked for the demodulate() call that follows (dem_base:548-632, 765-859)."""
+        self._as_chunk_buffer(samples)
+        (res, E, sym, centre, mag, means, bits, centres8, trust8, err) = self._engine.chunk_to_bits(
+            self._stitch, self.doppCyperSymNorm, self.clippedPeakIPure)
+        self._pending = None
+        self._bits_ready = (res, sym, centre, mag, bits, centres8, trust8, err)
+        return self._finish_search(res, E, means=means)
 
     # -- a5 --------------------------------------------------------------------------------------
     def findUHF(self, samples=None):
@@ -191,7 +208,7 @@ class Demodulator:
             self._pending = None
         return self._finish_search(res, E)
 
-    def _finish_search(self, res, E, wins=None):
+    def _finish_search(self, res, E, wins=None, means=None):
         """Host half of __findUHF (dem_base:604-632) on the device results of one chunk."""
         self.last = {"E": E.copy(), "res": np.array([res.best_idx, res.metric_db], dtype=np.float32),
                      "peak": (res.peak_val, res.peak_bin, res.peak_mask, res.peak_offset)}
@@ -204,13 +221,13 @@ class Demodulator:
         lowVal, highVal = self.doppHzLUT[lowIdx], self.doppHzLUT[highIdx]
         bestDopplerScaled = lowVal + (highVal - lowVal) * frac
         self.dopplerIdxlast = np.int32(res.shift)
-        SNR = self.computeSNR(lowIdx, highIdx, SNR_WINDOW, res, wins)
+        SNR = self.computeSNR(lowIdx, highIdx, SNR_WINDOW, res, wins, means)
         freqOffset = bestDopplerScaled - self.centreFreqOffset
         sdev_Hz = np.float64(res.metric_db) / self.Nfft * self.sampleRate
         return freqOffset, sdev_Hz, self.clippedPeakIPure, SNR
 
     # -- a10 -------------------------------------------------------------------------------------
-    def computeSNR(self, doppMatchLow, doppMatchHigh, windowWidth, res=None, given=None):
+    def computeSNR(self, doppMatchLow, doppMatchHigh, windowWidth, res=None, given=None, means=None):
         """SNR from the chunk spectrum around the found bins vs the same window half a band away
         (dem_base:635-667), evaluated with the reference's slicing rules on windows the device gathered."""
         N = self.Nfft
@@ -218,6 +235,9 @@ class Demodulator:
         hi = int(self.doppCyperSymNorm[doppMatchHigh])
         nlo, nhi = (lo + N // 2) % N, (hi + N // 2) % N
         wins = None
+        if means is not None:        # the library already averaged the two windows (common geometry, pcs_snr_means)
+            with np.errstate(all="ignore"):
+                return np.float64(20) * np.log10(np.float64(means[0] / means[1]) - 1)
         if res is not None and res.sig_len > 0 and windowWidth == SNR_WINDOW:
             sig, noise = given if given is not None else self._engine.snr_windows(res)
             # common case: neither window touches the ends of the spectrum, so the reference's slices
@@ -227,7 +247,7 @@ class Demodulator:
                     and res.sig_start == lo - w and res.noise_start == nlo - w
                     and len(sig) == hi - lo + 2 * w and len(noise) == nhi - nlo + 2 * w):
                 with np.errstate(all="ignore"):
-                    ratio = np.float32(np.mean(np.abs(sig))) / np.float32(np.mean(np.abs(noise)))
+                    ratio = _native.mean_abs_c64(sig) / _native.mean_abs_c64(noise)     # float32 / float32
                     return np.float64(20) * np.log10(np.float64(ratio) - 1)
             wins = ((res.sig_start, sig), (res.noise_start, noise))
         full = [None]
@@ -286,9 +306,20 @@ class Demodulator:
     def demodulateSTX(self):
         self.dopplerIdxlast = self.doppOffsetIdx          # dem_base:760
         self._pending = None
+        self._bits_ready = None
         return self.__demodulate()
 
     def __demodulate(self):
+        if self._bits_ready is not None:
+            res, idxSymbol, centres, magnitudes, bits, centres8, trust8, err = self._bits_ready
+            self._bits_ready = None
+            spSym = np.float64(res.sp_sym)
+            self.last.update(shift=int(res.demod_shift), timing=np.array(res.timing[:], dtype=np.float32), spSym=spSym,
+                             codeOffset=np.float64(res.code_offset), sym=idxSymbol.copy(), centres=centres.copy(),
+                             mag=magnitudes.copy())
+            if err is not None:
+                raise err
+            return bits, centres8, trust8, spSym
         if self._pending is not None:
             res, idxSymbol, centres, magnitudes = self._pending
             self._pending = None

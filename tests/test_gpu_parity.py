@@ -224,17 +224,91 @@ def test_host_postprocessing_exact_on_device_outputs(backend):
     assert (tagged > 0) == (backend == "STX")
 
 
-def test_fused_and_two_step_schedules_agree():
-    conf = load_conf("benchmark/bench_GMSK.json")
-    demA, _ = _demods(conf, fused=True)
-    demB, _ = _demods(conf, fused=False)
-    sig, _ = S.bench_stream("GMSK", 12, seed=5)
-    a, b = O.run_stream(demA, sig), O.run_stream(demB, sig)
-    for x, y in zip(a, b):
-        np.testing.assert_array_equal(x["data"], y["data"])
-        np.testing.assert_array_equal(x["trust"], y["trust"])
-        np.testing.assert_equal(x["doppler"], y["doppler"])
-        np.testing.assert_equal(x["SNR"], y["SNR"])       # NaN-aware
+@pytest.mark.parametrize("kw", [dict(search_form=2), dict(search_form=1), dict(items_per_cta=5), dict(items_per_cta=1000),
+                                dict(groups_per_cta=4, items_per_cta=7), dict(groups_per_cta=16, items_per_cta=33)])
+def test_search_forms_agree(kw):
+    """The shifted-filter form of the 256-point search (default), the rotate-the-chunk forms and every CTA tiling of the
+    former give the same energies and peaks (<= 2e-6: only fp32 rounding differs) and the same estimate; tilings of the
+    same form are bit-identical because each (bin, block) partial is computed by the same instruction sequence."""
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=14, doppCarrierSteps=24,
+                        noise_measure_offset_Hz=30000)          # noise row prepended: 25 rows
+    demA, orc = _demods(conf, fused=False)
+    demB, _ = _demods(conf, fused=False, **kw)
+    x = _noise_chunk(2 ** 14, 11, with_packet="GMSK")
+    out = []
+    for dem in (demA, demB):
+        dem.get_signalBufferHostPointer()[:] = x
+        dem.uploadToGPU(dem.get_signalBufferHostPointer())
+        res, E = dem._engine.search()
+        v, o = dem._engine.peaks()
+        out.append((res, E.copy(), v.copy(), o.copy()))
+    (ra, Ea, va, oa), (rb, Eb, vb, ob) = out
+    if "search_form" in kw:
+        assert rel_err(Eb, Ea) < 2e-6 and rel_err(vb, va) < 2e-6
+        assert np.mean(oa != ob) <= 0.02
+    else:
+        assert np.array_equal(Ea, Eb) and np.array_equal(va, vb) and np.array_equal(oa, ob)
+    assert (ra.shift, ra.low_idx, ra.high_idx) == (rb.shift, rb.low_idx, rb.high_idx)
+    Eo, pv, po = O.search_energy(O.forward_fft(x), orc.masks, orc.doppCyperSymNorm, orc.SUM_ALL_MASKS_PYTHON, want_peaks=True)
+    assert rel_err(Eb, Eo) < 1e-4 and rel_err(vb, pv) < 1e-4
+
+
+def test_search_bin_range_rows_equal_the_full_table():
+    """Bin sharding: rows [lo, hi) searched on their own are bit-identical to the same rows of the full search."""
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=14, doppCarrierSteps=24)
+    dem, _ = _demods(conf, fused=False)
+    eng = dem._engine
+    x = _noise_chunk(2 ** 14, 12, with_packet="GMSK")
+    import torch
+
+    dev = []
+    for ptr, typestr in zip(eng.shard_buffers(), ("<f4", "<f4", "<i4")):
+        class _W:
+            __cuda_array_interface__ = {"shape": (eng.D, eng.M), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev.append(torch.as_tensor(_W(), device="cuda:0"))
+
+    def tables():
+        torch.cuda.synchronize()
+        out = [t.cpu().numpy().copy() for t in dev]
+        for t in dev:
+            t.zero_()             # the next run must write its rows itself
+        torch.cuda.synchronize()
+        return out
+
+    dem.get_signalBufferHostPointer()[:] = x
+    eng.upload()
+    eng.enqueue_search_local()
+    E, v, o = tables()
+    assert np.all(E[:, 0] > 0)
+    for lo, hi in ((0, 7), (7, 19), (19, 24)):
+        eng.set_bin_range(lo, hi)
+        eng.upload()
+        eng.enqueue_search_local()
+        Es, vs, os_ = tables()
+        np.testing.assert_array_equal(Es[lo:hi], E[lo:hi])
+        np.testing.assert_array_equal(vs[lo:hi], v[lo:hi])
+        np.testing.assert_array_equal(os_[lo:hi], o[lo:hi])
+
+
+@pytest.mark.parametrize("mod,cfg", [("GMSK", "benchmark/bench_GMSK.json"), ("BPSK", "benchmark/bench_BPSK.json")])
+def test_fused_and_two_step_schedules_agree(mod, cfg):
+    """One native call per chunk (pcs_chunk_to_bits, default), fused device schedule + post-processing in demodulate(),
+    the reference's two-step schedule, and the NumPy post-processing mirror: identical outputs."""
+    conf = load_conf(cfg)
+    demA, _ = _demods(conf)
+    assert demA.one_call and demA.fused and demA._stitch is not None
+    others = [_demods(conf, one_call=False)[0], _demods(conf, fused=False)[0], _demods(conf, native_post=False)[0]]
+    sig, _ = S.bench_stream(mod, 12, seed=5)
+    a = O.run_stream(demA, sig)
+    assert len(a) > 5
+    for dem in others:
+        for x, y in zip(a, O.run_stream(dem, sig)):
+            np.testing.assert_array_equal(x["data"], y["data"])
+            np.testing.assert_array_equal(x["trust"], y["trust"])
+            np.testing.assert_equal(x["doppler"], y["doppler"])
+            np.testing.assert_equal(x["doppler_std"], y["doppler_std"])
+            np.testing.assert_equal(x["SNR"], y["SNR"])       # NaN-aware
+            assert x["spSymEst"] == y["spSymEst"]
 
 
 def test_search_is_bit_reproducible():

@@ -68,3 +68,17 @@ def test_bad_arguments_are_rejected_before_touching_the_device():
                         ctypes.byref(h))
     assert rc == -1 and b"ABI version" in lib.pcs_last_error()
     assert lib.pcs_destroy(None) == 0
+
+
+def test_window_mean_of_magnitudes_matches_numpy():
+    """pcs_mean_abs_c64 (the computeSNR window means, dem_base:657-661) against np.mean(np.abs(.)): equal to float32
+    rounding (NumPy's own result moves in the last ulp with the host's SIMD dispatch)."""
+    rng = np.random.RandomState(4)
+    for n in (1, 2, 7, 10, 170, 1000, 8192):
+        z = ((rng.randn(n) + 1j * rng.randn(n)) * 10.0 ** rng.uniform(-3, 3)).astype(np.complex64)
+        got = _native.mean_abs_c64(z)
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, np.mean(np.abs(z.astype(np.complex128))), rtol=2e-7)
+        np.testing.assert_allclose(got, np.mean(np.abs(z)), rtol=1e-6)
+    with pytest.raises(_native.NativeError):
+        _native.mean_abs_c64(np.zeros(0, np.complex64))
