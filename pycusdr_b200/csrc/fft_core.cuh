@@ -32,9 +32,14 @@ constexpr int padded_len(int n) { return n + (n >> 4); }
 // one; measured: tools/ubench/fp32x2.cu).
 PCS_DEVINL float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 PCS_DEVINL float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// A complex multiply is two packed instructions, FMUL2 + FFMA2: the broadcast of a.x / a.y ("R.F32"), the swap of b
+// ("R.F32x2.LO_HI") and the per-component sign of the addend ("-R.F32x2.HI_LO.NP") are all SASS operand modifiers.
+// Keeping every butterfly instruction packed matters beyond the issue slot it saves: a scalar FMUL between packed
+// instructions leaves half of the FMA pipe idle for a cycle (tools/ubench/fp32x2.cu: FADD2+FFMA costs 3.5 slots, not 3).
 PCS_DEVINL float2 cmul(float2 a, float2 b) {
-    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = fma2(a.x, b, (-a.y b.y, a.y b.x)); same roundings as two scalar fmas
-    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-a.y * b.y, a.y * b.x));
+    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = fma2(a.x, b, (-(a.y b.y), a.y b.x)); same roundings as two scalar fmas
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));
+    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
 }
 PCS_DEVINL float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // |z|^2 with the contraction nvcc applies to the reference's ComplexAbsSquared (FMUL + FFMA).
@@ -43,8 +48,9 @@ PCS_DEVINL float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
 // multiply by exp(i*DIR*theta) given c = cos(theta), s = sin(theta)
 template <int DIR>
 PCS_DEVINL float2 mulw(float2 v, float c, float s) {
-    if (DIR < 0) return __ffma2_rn(v, make_float2(c, c), make_float2(v.y * s, -v.x * s));
-    return __ffma2_rn(v, make_float2(c, c), make_float2(-v.y * s, v.x * s));
+    const float2 t = __fmul2_rn(make_float2(v.y, v.x), make_float2(s, s));
+    if (DIR < 0) return __ffma2_rn(v, make_float2(c, c), make_float2(t.x, -t.y));
+    return __ffma2_rn(v, make_float2(c, c), make_float2(-t.x, t.y));
 }
 // multiply by DIR*i
 template <int DIR>

@@ -195,8 +195,9 @@ struct Os256Params {
     float invN;
 };
 
-PCS_DEVINL float2 cmulc(float2 a, float2 b) {   // a * conj(b) = fma2(a, b.x, (a.y b.y, -a.x b.y))
-    return __ffma2_rn(a, make_float2(b.x, b.x), make_float2(a.y * b.y, -a.x * b.y));
+PCS_DEVINL float2 cmulc(float2 a, float2 b) {   // a * conj(b) = fma2(a, b.x, (a.y b.y, -(a.x b.y))): FMUL2 + FFMA2
+    const float2 t = __fmul2_rn(make_float2(b.y, b.y), make_float2(a.y, a.x));
+    return __ffma2_rn(a, make_float2(b.x, b.x), make_float2(t.x, -t.y));
 }
 
 // 256-point transform of one 16-lane group. In: v[r] = in[t + 16 r]. Out: slot s holds out[t + 16 dft_q<16>(s)].
@@ -477,14 +478,16 @@ __global__ void __launch_bounds__(G * 16, 32 / G) search_fs256_kernel(Fs256Param
             for (int m = 0; m < p.M; ++m) {
                 float2 v[16];
                 fs256_filter(s_g + (size_t)m * 128 + t, xb, buf, tw, t, v);
-                float sum = 0.f, best = 0.f;
+                float2 sum2 = make_float2(0.f, 0.f);      // even / odd slots accumulate side by side (one FADD2 per pair)
+                float best = 0.f;
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    const float mag = (vm >> s) & 1u ? cabs2(v[s]) : 0.f;
-                    sum += mag;
-                    best = fmaxf(best, mag);
+                for (int s = 0; s < 16; s += 2) {
+                    const float m0 = (vm >> s) & 1u ? cabs2(v[s]) : 0.f;
+                    const float m1 = (vm >> (s + 1)) & 1u ? cabs2(v[s + 1]) : 0.f;
+                    sum2 = __fadd2_rn(sum2, make_float2(m0, m1));
+                    best = fmaxf(best, fmaxf(m0, m1));
                 }
-                acc_sum[m * 17 + t] = sum;    // per-lane partials parked in shared memory: no cross-lane traffic in the loop
+                acc_sum[m * 17 + t] = sum2.x + sum2.y;   // per-lane partials parked in shared memory: no cross-lane traffic in the loop
                 acc_max[m * 17 + t] = best;
             }
             __syncwarp();
