@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--search-form", type=int, default=0,
                     help="256-point search: 0 shifted filters (default), 1 / 2 rotate-the-chunk comparison variants")
     ap.add_argument("--items-per-cta", type=int, default=0, help="tuning knob of the shifted-filter search kernel")
+    ap.add_argument("--warps20", action="store_true", help="tuning knob: 96-register build of the shifted-filter kernel")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=0,
@@ -425,7 +426,7 @@ def main():
     ring_bytes = dev_chunks.numel() * 8
 
     knobs = dict(groups_per_cta=args.groups_per_cta, xb_smem=args.xb_smem, search_form=args.search_form,
-                 items_per_cta=args.items_per_cta)
+                 items_per_cta=args.items_per_cta, warps20=args.warps20)
     dem = UHF.Demodulator(conf, protocol, RADIO, log2_block=args.log2_block, **knobs)
     eng = dem._engine
     D, M = eng.D, eng.M

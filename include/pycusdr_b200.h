@@ -59,7 +59,7 @@ typedef struct {
     int32_t log2_block;              /* 0 = choose; else force the overlap-save block size 2**log2_block */
     int32_t snr_window;              /* half width of the computeSNR windows (5)    dem_base:620 */
     int32_t reserved[3];             /* tuning knobs, all 0 by default.  [0] bit 0: 1 = never replay the per-chunk sequence as a
-                                        CUDA graph; [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
+                                        CUDA graph, bit 1: 96-register build of the shifted-filter kernel (20 warps per SM); [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
                                         8+: (bin, block) items per CTA of the shifted-filter search kernel (0 = 64); [2] form of the
                                         256-point search: 0 = shifted filters (block spectra shared by all bins), 1 / 2 = rotate the
                                         chunk per bin with the block spectrum in shared memory / registers (comparison variants) */

@@ -428,8 +428,8 @@ PCS_DEVINL unsigned fs256_valid_mask(int Lpos, int vlen, int t) {
     return vm;
 }
 
-template <int G>     // G = groups (half warps) per CTA
-__global__ void __launch_bounds__(G * 16, 32 / G) search_fs256_kernel(Fs256Params p) {
+template <int G, int WARPS_PER_SM = 16>     // G = groups (half warps) per CTA; WARPS_PER_SM sets the register budget
+__global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_kernel(Fs256Params p) {
     __shared__ float2 sbuf[G][272];
     extern __shared__ float4 s_dyn[];         // [M][128] float4 filter spectra of the current bin | [G][2][M][17] float partials
     float4* s_g = s_dyn;

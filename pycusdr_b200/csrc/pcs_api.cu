@@ -88,7 +88,7 @@ struct pcs_handle {
     float4* d_gperm = nullptr;
     bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
     float4 *d_xbs = nullptr, *d_gs = nullptr;
-    int fs_items = 64;                 // items (bin, block) per CTA
+    int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
     int* d_part_blk = nullptr;
     float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
@@ -438,8 +438,7 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
         shifted_filters256_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_masks, h->d_shifts, h->d_gs, N, D, M);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        const int ipc = h->cfg.reserved[1] >> 8;
-        h->fs_items = ipc > 0 ? ipc : 64;
+        h->fs_items = h->cfg.reserved[1] >> 8;      // 0 = choose per launch
         h->fs256 = true;
     }
     return 0;
@@ -664,7 +663,7 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
     info->support_neg = h->Lneg;
     const int gk = h->cfg.reserved[1] & 0xff, g256 = gk == 16 ? 16 : gk == 4 ? 4 : 8;
     info->groups_per_cta = h->fast256 ? g256 : h->G;
-    info->search_ctas = h->fs256 ? (int)(((long long)h->nblk256 * h->D + h->fs_items - 1) / h->fs_items)
+    info->search_ctas = h->fs256 ? h->search_ctas          // of the last launch (the tiling adapts to the bin range)
                         : h->fast256 ? (int)(((long long)h->nblk256 * h->D + g256 - 1) / g256)
                                      : (int)(((long long)h->nblk * h->D + h->G - 1) / h->G);
     info->search_smem_bytes = h->search_smem;
@@ -705,15 +704,21 @@ static int enqueue_search_local256(pcs_handle* h) {
         CUDA_TRY(cudaGetLastError());
         Fs256Params q{};
         q.xbs = h->d_xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = p.psum; q.pmax = p.pmax;
-        q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos; q.items_per_cta = h->fs_items;
+        q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos;
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
+        // items per CTA: 64 amortises the per-CTA set-up (twiddles, the bin's 2 KB x M filter spectra); small searches
+        // (short chunks, a rank's slice of the bins) get smaller CTAs so that the grid still covers >= 4 waves
+        q.items_per_cta = h->fs_items > 0 ? h->fs_items
+                                          : (int)std::min<long long>(64, std::max<long long>(G, items / (16LL * h->sm_count) / G * G));
         h->search_ctas = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
         const size_t dyn = (size_t)p.M * 128 * sizeof(float4) + (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + dyn);
-        static size_t configured[PCS_MAX_DEVICES][3] = {};
-        const int gi = G == 16 ? 0 : G == 8 ? 1 : 2;
-        auto kern = G == 16 ? search_fs256_kernel<16> : G == 8 ? search_fs256_kernel<8> : search_fs256_kernel<4>;
+        static size_t configured[PCS_MAX_DEVICES][4] = {};
+        const bool occ20 = (h->cfg.reserved[0] & 2) && G == 8;   // tuning knob: 96-register build, 5 CTAs (20 warps) per SM
+        const int gi = occ20 ? 3 : G == 16 ? 0 : G == 8 ? 1 : 2;
+        auto kern = occ20 ? search_fs256_kernel<8, 20> : G == 16 ? search_fs256_kernel<16> : G == 8 ? search_fs256_kernel<8>
+                                                                                            : search_fs256_kernel<4>;
         if (configured[h->cfg.device][gi] < dyn) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             configured[h->cfg.device][gi] = dyn;

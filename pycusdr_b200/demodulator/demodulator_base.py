@@ -38,7 +38,8 @@ SNR_WINDOW = 5              # dem_base:620
 class Demodulator:
 
     def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True,
-                 native_post=True, groups_per_cta=0, xb_smem=False, search_form=0, items_per_cta=0, one_call=True):
+                 native_post=True, groups_per_cta=0, xb_smem=False, search_form=0, items_per_cta=0, one_call=True,
+                 warps20=False):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
@@ -127,7 +128,7 @@ class Demodulator:
             window_width=self.windowWidth, sum_all_masks=self.SUM_ALL_MASKS_PYTHON,
             code_search_mask_offset=self.CODE_SEARCH_MASK_OFFSET, samples_per_sym=self.spsym, path=path,
             log2_block=log2_block, snr_window=SNR_WINDOW, use_graph=use_graph, groups_per_cta=groups_per_cta, xb_smem=xb_smem,
-            search_form=search_form, items_per_cta=items_per_cta)
+            search_form=search_form, items_per_cta=items_per_cta, warps20=warps20)
         self._engine = _native.Engine(**self._engine_kwargs)
         self.GPU_bufSignalTime_cpu_handle = self._engine.host_buffer
         # bit extraction + chunk stitching + trust tagging in one native call (the NumPy methods below stay as the
