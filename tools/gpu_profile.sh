@@ -15,6 +15,6 @@ $SMALL > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launch_$TAG.log 2>&1
 echo "ncu launches rc=$?"
 $SMALL > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:search_os -s 4 -c 2 -f -o $OUT/prof_search_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:search_ -s 4 -c 2 -f -o $OUT/prof_search_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 cat $OUT/bench_$TAG.json | head -c 3000
