@@ -103,6 +103,16 @@ void* pcs_host_buffer(pcs_handle* h);
  * forward FFT.  Returns without synchronising. */
 int pcs_upload(pcs_handle* h);
 
+/* Replaces __thresholdInput followed by uploadToGPU (STX backend: STX.py:13-20, dem_base:670-707, 548-558): the pinned
+ * chunk is copied to HBM, clipped there in two passes to scale * mean(|x|) (scale = peakThresholdScale; the means are
+ * float32 pairwise sums in np.mean's order), and copied back into the pinned buffer, which the reference clips in
+ * place and whose tail the caller carries into the next chunk (demodulator_process.py:337).  clipped_idx receives the
+ * ascending indices of the samples clipped by the second pass (clippedPeakIPure, dem_base:683-684), at most cap of
+ * them; *n_clipped is their full count.  thresholds (float[2], may be NULL) = the two clip levels.  Synchronises.
+ * nfft <= 2^22. */
+int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int32_t cap, int32_t* n_clipped,
+                           float* thresholds);
+
 /* Same, but the chunk is already in HBM (device pointer to complex64[nfft]); no copy is made and the
  * buffer must stay valid until the next synchronising call. */
 int pcs_upload_device(pcs_handle* h, const void* d_chunk);

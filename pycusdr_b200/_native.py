@@ -58,6 +58,7 @@ SYMBOLS = {
     "pcs_destroy": (C.c_int, [_P]),
     "pcs_host_buffer": (_P, [_P]),
     "pcs_upload": (C.c_int, [_P]),
+    "pcs_upload_thresholded": (C.c_int, [_P, C.c_float, _P, C.c_int32, C.POINTER(C.c_int32), _P]),
     "pcs_upload_device": (C.c_int, [_P, _P]),
     "pcs_search": (C.c_int, [_P, C.POINTER(Result), _P]),
     "pcs_demod": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P]),
@@ -357,6 +358,17 @@ class Engine:
     # -- per chunk ------------------------------------------------------------------------------
     def upload(self):
         self._check(self.lib.pcs_upload(self._h))
+
+    def upload_thresholded(self, scale):
+        """``__thresholdInput`` + ``uploadToGPU`` on the device (pcs_upload_thresholded): the pinned chunk ends up clipped
+        in place; returns (indices clipped by the second pass, the two float32 clip levels)."""
+        if getattr(self, "_clip_idx", None) is None:
+            self._clip_idx = np.empty(self.nfft, dtype=np.int64)
+            self._clip_thr = np.empty(2, dtype=np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.pcs_upload_thresholded(self._h, float(scale), _ptr(self._clip_idx), self.nfft, C.byref(n),
+                                                    _ptr(self._clip_thr)))
+        return self._clip_idx[:n.value].copy(), self._clip_thr.copy()
 
     def upload_device(self, dev_ptr):
         self._check(self.lib.pcs_upload_device(self._h, _P(dev_ptr)))

@@ -1278,6 +1278,102 @@ __global__ void __launch_bounds__(1024) parseval_reduce_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// a19 __thresholdInput (dem_base:670-707) on the device: two passes of "clip everything above
+// peakThresholdScale * mean(|x|) back onto that radius".  The mean is np.mean's: float32 pairwise summation in NumPy's
+// own order (leaves of 128 samples, eight strided accumulators per leaf combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+// then a balanced tree over the leaves -- loops_utils.h.src: pairwise_sum), so for a power-of-two chunk the threshold
+// is the float32 NumPy computes from the same magnitudes.  The clip is thresh * (x / |x|) with NumPy's complex-by-real
+// arithmetic: x * fl(1/|x|), then * thresh, every product rounded to float32.
+// ---------------------------------------------------------------------------------------------
+// Sum of 1024 floats in shared memory in NumPy's pairwise order; 128 threads; result valid in thread 0.
+PCS_DEVINL float np_pairwise_sum_1024(const float* s, float* scratch) {
+    float r = 0.f;
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const float* leaf = s + (tid >> 3) * 128 + (tid & 7);
+        r = leaf[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) r = __fadd_rn(r, leaf[8 * i]);
+#pragma unroll
+        for (int o = 1; o <= 16; o <<= 1) r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, o));   // within leaf, then leaves 2 by 2
+        if (tid == 32) scratch[0] = r;
+    }
+    __syncthreads();
+    if (tid == 0) r = __fadd_rn(r, scratch[0]);
+    return r;
+}
+
+// pass 0: |x| and the per-1024 partial sums.
+__global__ void __launch_bounds__(128) threshold_abs_kernel(const float2* __restrict__ x, float* __restrict__ mag,
+                                                            float* __restrict__ partial) {
+    __shared__ float s[1024];
+    __shared__ float scratch[1];
+    const size_t base = (size_t)blockIdx.x * 1024;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float2 v = x[base + threadIdx.x + 128 * k];
+        const float m = hypotf(v.x, v.y);
+        s[threadIdx.x + 128 * k] = m;
+        mag[base + threadIdx.x + 128 * k] = m;
+    }
+    __syncthreads();
+    const float r = np_pairwise_sum_1024(s, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// thresh = float32(scale) * (pairwise total / N): balanced tree over nb (power of two, <= 4096) partials.
+__global__ void __launch_bounds__(1024) threshold_level_kernel(const float* __restrict__ partial, int nb, float scale, float invN,
+                                                               float* __restrict__ thresh) {
+    __shared__ float s[4096];
+    for (int i = threadIdx.x; i < nb; i += 1024) s[i] = partial[i];
+    __syncthreads();
+    for (int stride = 1; stride < nb; stride <<= 1) {
+        for (int i = threadIdx.x * 2 * stride; i + stride < nb; i += 2048 * stride) s[i] = __fadd_rn(s[i], s[i + stride]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *thresh = __fmul_rn(scale, __fmul_rn(__fadd_rn(0.f, s[0]), invN));
+}
+
+// pass 1 (LAST = false): clip, refresh |x| of the clipped samples, partial sums of the refreshed magnitudes;
+// pass 2 (LAST = true): clip and mark the clipped samples in a bit mask (clippedPeakIPure).
+template <bool LAST>
+__global__ void __launch_bounds__(128) threshold_clip_kernel(float2* __restrict__ x, float* __restrict__ mag,
+                                                             const float* __restrict__ thresh, float* __restrict__ partial,
+                                                             unsigned int* __restrict__ bits) {
+    __shared__ float s[1024];
+    __shared__ float scratch[1];
+    const float thr = *thresh;
+    const size_t base = (size_t)blockIdx.x * 1024;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const size_t n = base + threadIdx.x + 128 * k;
+        float m = mag[n];
+        const bool over = m > thr;
+        if (over) {
+            const float2 v = x[n];
+            const float rcp = __frcp_rn(m);
+            const float2 w = make_float2(__fmul_rn(thr, __fmul_rn(v.x, rcp)), __fmul_rn(thr, __fmul_rn(v.y, rcp)));
+            x[n] = w;
+            if (!LAST) {
+                m = hypotf(w.x, w.y);
+                mag[n] = m;
+            }
+        }
+        if (LAST) {
+            const unsigned int word = __ballot_sync(0xffffffffu, over);
+            if ((threadIdx.x & 31) == 0) bits[n >> 5] = word;
+        } else {
+            s[threadIdx.x + 128 * k] = m;
+        }
+    }
+    if (!LAST) {
+        __syncthreads();
+        const float r = np_pairwise_sum_1024(s, scratch);
+        if (threadIdx.x == 0) partial[blockIdx.x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Peer exchange (bin sharding over NVLink): arrival flags in the owner's exchange region.
 // ---------------------------------------------------------------------------------------------
 __global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {

@@ -86,6 +86,8 @@ struct pcs_handle {
     bool fast256 = false;
     int nblk256 = 0, V256 = 0;
     float4* d_gperm = nullptr;
+    float *d_thr_partial = nullptr, *d_thr_level = nullptr;   // pcs_upload_thresholded (allocated on first use)
+    unsigned int *d_thr_bits = nullptr, *h_thr_bits = nullptr;
     bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
     float4 *d_xbs = nullptr, *d_gs = nullptr;
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
@@ -488,7 +490,7 @@ int pcs_destroy(pcs_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side) cudaStreamSynchronize(h->side);
     for (void* p : h->dev_allocs) cudaFree(p);
-    void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre};
+    void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre, h->h_thr_bits};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
     for (int r = 0; r < h->peer_world; ++r)
@@ -1055,6 +1057,55 @@ int pcs_upload(pcs_handle* h) {
     h->searched = h->demodulated = false;
     h->spectrum_pending = true;        // enqueued with the estimate (eager) or on the graph's side branch
     h->spectrum_full = false;
+    return PCS_OK;
+}
+
+// a19 + a4 for the STX backend (STX.py:13-20, dem_base:670-707): the chunk goes to HBM, is clipped there (five small
+// kernels, thresholds by NumPy's own summation order), and comes back into the pinned buffer because the caller carries
+// raw[-overlap:] into the next chunk (demodulator_process.py:337) and the reference clips in place.
+int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int32_t cap, int32_t* n_clipped,
+                           float* thresholds) {
+    if (!h || !n_clipped || (cap > 0 && !clipped_idx) || cap < 0) return fail(PCS_ERR_INVALID, "bad argument");
+    const int N = h->N, nb = N / 1024;
+    if (nb > 4096) return fail(PCS_ERR_INVALID, "pcs_upload_thresholded supports nfft <= 2^22");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->d_thr_partial) {
+        if (int rc = dev_alloc(h, &h->d_thr_partial, (size_t)nb)) return rc;
+        if (int rc = dev_alloc(h, &h->d_thr_level, (size_t)2)) return rc;
+        if (int rc = dev_alloc(h, &h->d_thr_bits, (size_t)N / 32)) return rc;
+        CUDA_TRY(cudaHostAlloc((void**)&h->h_thr_bits, sizeof(unsigned int) * (N / 32) + 2 * sizeof(float), cudaHostAllocDefault));
+    }
+    float* mag = h->d_p;      // free until the demod stage of this chunk writes it
+    CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
+    threshold_abs_kernel<<<nb, 128, 0, h->stream>>>(h->d_x, mag, h->d_thr_partial);
+    threshold_level_kernel<<<1, 1024, 0, h->stream>>>(h->d_thr_partial, nb, scale, 1.0f / (float)N, h->d_thr_level);
+    threshold_clip_kernel<false><<<nb, 128, 0, h->stream>>>(h->d_x, mag, h->d_thr_level, h->d_thr_partial, nullptr);
+    threshold_level_kernel<<<1, 1024, 0, h->stream>>>(h->d_thr_partial, nb, scale, 1.0f / (float)N, h->d_thr_level + 1);
+    threshold_clip_kernel<true><<<nb, 128, 0, h->stream>>>(h->d_x, mag, h->d_thr_level + 1, nullptr, h->d_thr_bits);
+    h->launches += 5;
+    CUDA_TRY(cudaGetLastError());
+    float* h_levels = reinterpret_cast<float*>(h->h_thr_bits + N / 32);
+    CUDA_TRY(cudaMemcpyAsync(h->h_thr_bits, h->d_thr_bits, sizeof(unsigned int) * (N / 32), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_levels, h->d_thr_level, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(float2) * N, cudaMemcpyDeviceToHost, h->stream));
+    h->d_x_cur = h->d_x;
+    h->uploaded = true;
+    h->searched = h->demodulated = false;
+    h->spectrum_pending = true;
+    h->spectrum_full = false;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int n = 0;
+    for (int w = 0; w < N / 32; ++w) {
+        unsigned int word = h->h_thr_bits[w];
+        while (word) {
+            const int b = __builtin_ctz(word);
+            word &= word - 1;
+            if (n < cap) clipped_idx[n] = (int64_t)w * 32 + b;
+            ++n;
+        }
+    }
+    *n_clipped = n;       // may exceed cap: the caller then knows the list was truncated
+    if (thresholds) { thresholds[0] = h_levels[0]; thresholds[1] = h_levels[1]; }
     return PCS_OK;
 }
 

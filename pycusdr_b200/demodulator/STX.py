@@ -7,8 +7,11 @@ class Demodulator(Demodulator_base):
 
     def uploadAndFindCarrier(self, samples):
         samples = self._as_chunk_buffer(samples)
-        self.thresholdInput(samples)
-        self.uploadToGPU(samples)
+        if self.native_threshold and self.Nfft <= 2 ** 22:
+            self.thresholdAndUpload(samples)        # clipping on the device, same in-place result
+        else:
+            self.thresholdInput(samples)
+            self.uploadToGPU(samples)
         return 0, 0, self.clippedPeakIPure, 0
 
     def demodulate(self):

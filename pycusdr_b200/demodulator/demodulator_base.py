@@ -39,13 +39,14 @@ class Demodulator:
 
     def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True,
                  native_post=True, groups_per_cta=0, xb_smem=False, search_form=0, items_per_cta=0, one_call=True,
-                 warps20=False):
+                 warps20=False, native_threshold=True):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
         self.confGPU = confGPU = conf["GPU"][confRadio["CUDA_settings"]]
         self.fused = fused
         self.one_call = one_call
+        self.native_threshold = native_threshold      # STX backend: input clipping on the device
 
         # chunk geometry (dem_base:89-93)
         self.sigLen = 2 ** confGPU["blockSize"]
@@ -180,6 +181,15 @@ class Demodulator:
     def thresholdInput(self, samples):
         self.__thresholdInput(samples)
 
+    def thresholdAndUpload(self, samples):
+        """__thresholdInput + uploadToGPU with the clipping done on the device (``pcs_upload_thresholded``); the pinned
+        buffer ends up clipped in place exactly as the reference leaves it (dem_base:670-707, 548-558)."""
+        self._as_chunk_buffer(samples)
+        over, self.clipLevels = self._engine.upload_thresholded(np.float32(self.peakThresholdScale))
+        self._pending = None
+        self._bits_ready = None
+        self._set_clipped(over)
+
     def uploadAndFindUHF(self, samples):
         samples = self._as_chunk_buffer(samples)
         self.__thresholdInput(samples)
@@ -287,6 +297,10 @@ class Demodulator:
             samples[over] = thresh * (samples[over] / mag[over])
             if rnd == 0:
                 mag[over] = np.abs(samples[over])
+        self._set_clipped(over)
+
+    def _set_clipped(self, over):
+        """clippedPeakIPure / clippedPeakI from the indices the second pass clipped (dem_base:683-705)."""
         self.clippedPeakIPure = over
         if len(over) > 0:
             self.peakMinGap = 100

@@ -340,6 +340,74 @@ def test_stx_backend_matches_oracle():
     np.testing.assert_array_equal(dem.clippedPeakIPure, orc.clippedPeakIPure)
 
 
+def _stx_pair(blockSize=15, scale=4.5):
+    from pycusdr_b200.demodulator import STX
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=blockSize)
+    conf["GPU"]["UHF"]["peakThresholdScale"] = scale
+    P = protocol_for(conf)
+    return STX.Demodulator(conf, P, RADIO), STX.Demodulator(conf, P, RADIO, native_threshold=False)
+
+
+@pytest.mark.parametrize("blockSize", [12, 15, 18])
+def test_device_threshold_is_numpy_exact_when_magnitudes_are(blockSize):
+    """pcs_upload_thresholded (a19, dem_base:670-707) on samples whose magnitude is exact in any implementation (one
+    component zero): clip levels (np.mean's pairwise float32 order), clipped indices and the clipped pinned buffer must be
+    bit-identical to the NumPy statement of the reference."""
+    dev, host = _stx_pair(blockSize)
+    N = dev.Nfft
+    rng = np.random.RandomState(blockSize)
+    x = np.zeros(N, np.complex64)
+    x.real[::2] = rng.randn(N // 2).astype(np.float32)
+    x.imag[1::2] = rng.randn(N // 2).astype(np.float32)
+    for pos, val in ((100, 40.0), (101, -35.0j), (150, 25.0), (N // 2, 1e3j), (N - 3, -77.0), (N - 2, 9.5j)):
+        x[pos] = np.complex64(val)
+    for d in (dev, host):
+        d.get_signalBufferHostPointer()[:] = x
+        d.uploadAndFindCarrier(d.get_signalBufferHostPointer())
+    a, b = dev.get_signalBufferHostPointer(), host.get_signalBufferHostPointer()
+    assert len(host.clippedPeakIPure) >= 5
+    np.testing.assert_array_equal(dev.clippedPeakIPure, host.clippedPeakIPure)
+    np.testing.assert_array_equal(dev.clippedPeakI, host.clippedPeakI)
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    # the second clip level is what NumPy computes from the (identical) clipped magnitudes of pass one
+    mag = np.abs(x)
+    t1 = np.float32(4.5) * np.mean(mag)
+    assert dev.clipLevels[0] == t1
+    # and the device copy of the chunk is the clipped one (what the demod stage then works on)
+    np.testing.assert_array_equal(dev.demodulate()[0], host.demodulate()[0])
+
+
+def test_device_threshold_matches_numpy_on_a_stream():
+    """General complex samples: magnitudes differ in the last ulp between hypotf and np.abs, so the clip levels agree to
+    float32 rounding; bursts far above the level give identical index lists, samples agree to 1e-6, bits are identical."""
+    dev, host = _stx_pair()
+    sig, _ = S.bench_stream("GMSK", 15, seed=3)
+    sig = sig.copy()
+    sig[40000:40003] *= 60
+    sig[70000:70200:7] *= 45
+    N, ovl = dev.Nfft, dev.sigOverlap
+    ra, rb = dev.get_signalBufferHostPointer(), host.get_signalBufferHostPointer()
+    ra[:] = 0
+    rb[:] = 0
+    clipped = 0
+    for c in range(len(sig) // (N - ovl)):
+        blk = sig[c * (N - ovl):(c + 1) * (N - ovl)]
+        ra[ovl:] = blk
+        rb[ovl:] = blk
+        dev.uploadAndFindCarrier(ra)
+        host.uploadAndFindCarrier(rb)
+        np.testing.assert_array_equal(dev.clippedPeakIPure, host.clippedPeakIPure)
+        np.testing.assert_allclose(ra.view(np.float32), rb.view(np.float32), rtol=1e-6, atol=1e-7)
+        a, b = dev.demodulate(), host.demodulate()
+        if c > 0:
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[2], b[2])
+        clipped += len(dev.clippedPeakIPure)
+        ra[:ovl] = ra[-ovl:]
+        rb[:ovl] = rb[-ovl:]
+    assert clipped > 30
+
+
 def test_graph_replay_and_eager_launches_agree():
     """The per-chunk sequence replayed as a CUDA graph must give the very same bytes as launching it kernel by kernel."""
     conf = load_conf("benchmark/bench_GMSK.json")
