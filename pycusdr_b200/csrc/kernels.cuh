@@ -206,11 +206,24 @@ template <int DIR>
 PCS_DEVINL void fft256_regs(float2* v, float2* buf, const float2* tw, int t) {
     Dft<16, DIR>::run(v);
     __syncwarp();                      // previous transform's loads are done before the buffer is overwritten
+    // Exchange through the group's 272-float2 buffer: element (storing lane r, output q) = natural index 16 r + q lives
+    // at 34 (r >> 1) + 2 q + (r & 1), so that the loading lane t finds its inputs t + 16 (2j) and t + 16 (2j + 1) side by
+    // side: 16 STS.64 + 8 LDS.128 per transform, both conflict-free (row stride 68 words = 4 mod 32).
+    {
+        float2* row = buf + 34 * (t >> 1) + (t & 1);
 #pragma unroll
-    for (int s = 0; s < 16; ++s) buf[17 * t + dft_q<16>(s)] = v[s];      // natural index 16 t + q, padded
+        for (int s = 0; s < 16; ++s) row[2 * dft_q<16>(s)] = v[s];
+    }
     __syncwarp();
+    {
+        const float4* col = reinterpret_cast<const float4*>(buf) + t;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = buf[t + 17 * r];                 // natural index t + 16 r, padded
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = col[17 * j];
+            v[2 * j] = make_float2(q.x, q.y);
+            v[2 * j + 1] = make_float2(q.z, q.w);
+        }
+    }
 #pragma unroll
     for (int r = 1; r < 16; ++r) v[r] = DIR < 0 ? cmul(v[r], tw[r]) : cmulc(v[r], tw[r]);
     Dft<16, DIR>::run(v);
@@ -289,7 +302,7 @@ PCS_DEVINL unsigned os256_valid_mask(const Os256Params& p, const Os256Item& it, 
 // XBS: keep the block spectrum in shared memory (fewer registers -> more resident warps) instead of registers.
 template <int G, bool XBS>     // G = groups (half warps) per CTA
 __global__ void __launch_bounds__(G * 16, XBS ? 40 / G : 32 / G) search_os256_kernel(Os256Params p) {
-    __shared__ float2 sbuf[G][272];
+    __shared__ __align__(16) float2 sbuf[G][272];
     __shared__ float2 sxb[XBS ? G : 1][XBS ? 256 : 1];
     extern __shared__ float s_acc[];          // [G groups][2][M][17]: per-lane sum / max of every mask
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
@@ -370,7 +383,7 @@ struct Fs256Params {
 // Block spectra of the chunk: block b = FFT_256(x[(b V - Lpos + i) % N], i = 0..255), one 16-lane group per block.
 __global__ void __launch_bounds__(256) block_spectra256_kernel(const float2* __restrict__ x, const float2* __restrict__ twg,
                                                                float4* __restrict__ xbs, int N, int nblk, int V, int Lpos) {
-    __shared__ float2 sbuf[16][272];
+    __shared__ __align__(16) float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2 tw[16];
 #pragma unroll
@@ -430,7 +443,7 @@ PCS_DEVINL unsigned fs256_valid_mask(int Lpos, int vlen, int t) {
 
 template <int G, int WARPS_PER_SM = 16>     // G = groups (half warps) per CTA; WARPS_PER_SM sets the register budget
 __global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_kernel(Fs256Params p) {
-    __shared__ float2 sbuf[G][272];
+    __shared__ __align__(16) float2 sbuf[G][272];
     extern __shared__ float4 s_dyn[];         // [M][128] float4 filter spectra of the current bin | [G][2][M][17] float partials
     float4* s_g = s_dyn;
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
@@ -575,7 +588,7 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
                                                                 unsigned long long* arrival_flag,
                                                                 unsigned long long arrival_value,
                                                                 const float4* __restrict__ xbs, const float4* __restrict__ gs) {
-    __shared__ float2 sbuf[16][272];
+    __shared__ __align__(16) float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
     float2 tw[16];
@@ -926,7 +939,7 @@ struct Demod256Params {
 };
 
 __global__ void __launch_bounds__(64) demod_os256_kernel(Demod256Params q) {
-    __shared__ float2 sbuf[4][272];
+    __shared__ __align__(16) float2 sbuf[4][272];
     const Os256Params& p = q.os;
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
@@ -1282,8 +1295,8 @@ __global__ void __launch_bounds__(1024) parseval_reduce_kernel(const float* __re
 // peakThresholdScale * mean(|x|) back onto that radius".  The mean is np.mean's: float32 pairwise summation in NumPy's
 // own order (leaves of 128 samples, eight strided accumulators per leaf combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
 // then a balanced tree over the leaves -- loops_utils.h.src: pairwise_sum), so for a power-of-two chunk the threshold
-// is the float32 NumPy computes from the same magnitudes.  The clip is thresh * (x / |x|) with NumPy's complex-by-real
-// arithmetic: x * fl(1/|x|), then * thresh, every product rounded to float32.
+// is the float32 NumPy computes from the same magnitudes.  The clip is thresh * (x / |x|) with NumPy's complex
+// arithmetic (x * fl(1/|x|), then * thresh, every operation rounded to float32).
 // ---------------------------------------------------------------------------------------------
 // Sum of 1024 floats in shared memory in NumPy's pairwise order; 128 threads; result valid in thread 0.
 PCS_DEVINL float np_pairwise_sum_1024(const float* s, float* scratch) {
@@ -1351,8 +1364,15 @@ __global__ void __launch_bounds__(128) threshold_clip_kernel(float2* __restrict_
         const bool over = m > thr;
         if (over) {
             const float2 v = x[n];
-            const float rcp = __frcp_rn(m);
-            const float2 w = make_float2(__fmul_rn(thr, __fmul_rn(v.x, rcp)), __fmul_rn(thr, __fmul_rn(v.y, rcp)));
+            // NumPy's complex64 / (m + 0i): rat = 0 / m, scl = 1 / (m + 0 * rat), q = ((re + im rat) scl, (im - re rat) scl);
+            // then (thr + 0i) * q = (thr q.re - 0 q.im, thr q.im + 0 q.re).  Spelled out term by term so that signed
+            // zeros and non-finite samples come out as they do there.
+            const float rat = __fdiv_rn(0.f, m);
+            const float scl = __frcp_rn(__fadd_rn(m, __fmul_rn(0.f, rat)));
+            const float qr = __fmul_rn(__fadd_rn(v.x, __fmul_rn(v.y, rat)), scl);
+            const float qi = __fmul_rn(__fsub_rn(v.y, __fmul_rn(v.x, rat)), scl);
+            const float2 w = make_float2(__fsub_rn(__fmul_rn(thr, qr), __fmul_rn(0.f, qi)),
+                                         __fadd_rn(__fmul_rn(thr, qi), __fmul_rn(0.f, qr)));
             x[n] = w;
             if (!LAST) {
                 m = hypotf(w.x, w.y);
