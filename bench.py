@@ -705,7 +705,8 @@ def main():
     s_ms, s_cnt = prof["search"]
     search_ms = s_ms / max(s_cnt, 1)
     roof = {
-        "bound": "fp32", "kernel": "search_os256_kernel" if plan["log2_block"] == 8 else "search_os_kernel",
+        "bound": "fp32", "kernel": ("search_fs256_kernel" if (args.search_form == 0 and not args.xb_smem and M <= 16)
+                                     else "search_os256_kernel") if plan["log2_block"] == 8 else "search_os_kernel",
         "achieved": k_flop / (search_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": k_flop / (search_ms * 1e-3) / 1e12 / fp32_peak,
         "peak_source": "measured FMA loop on this GPU (pcs_measure_fp32_peak); nominal 74.4",
@@ -718,6 +719,14 @@ def main():
         "chunk_frac": max(F_alg / (fp32_peak * 1e12), B_alg / (hbm_peak * 1e9)) * 1e3 / ms_step if world == 1 else None,
         "traffic": None,
     }
+    if roof["kernel"] == "search_fs256_kernel" and world == 1:
+        # what the hardware executes (DESIGN.md "Instruction mix"): 489 FMA-pipe lane-slots per filtered 256-point transform
+        # and lane (SASS count), 16 lanes per transform, M transforms per (bin, block) item
+        slots = float(plan["num_blocks"]) * Dl * M * 16 * 489
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        roof["executed_fma_pipe_frac"] = slots / (148 * 128 * clk * 1e6 * search_ms * 1e-3)
+        roof["executed_note"] = ("frac uses the survey's 5 N log2 N flop convention for the reference's Nfft-point transforms; "
+                                 "executed_fma_pipe_frac = FMA-pipe lane-slots the kernel's SASS issues / slots available in kernel_ms")
     try:        # DRAM bytes of one launch of this kernel from the committed ncu --set full capture (same workload, 1 GPU)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f).get(roof["kernel"])

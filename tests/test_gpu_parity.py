@@ -374,7 +374,9 @@ def test_device_threshold_is_numpy_exact_when_magnitudes_are(blockSize):
     t1 = np.float32(4.5) * np.mean(mag)
     assert dev.clipLevels[0] == t1
     # and the device copy of the chunk is the clipped one (what the demod stage then works on)
-    np.testing.assert_array_equal(dev.demodulate()[0], host.demodulate()[0])
+    a, b = dev.demodulate(), host.demodulate()
+    for u, v in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(u, v)
 
 
 def test_device_threshold_matches_numpy_on_a_stream():
@@ -401,7 +403,8 @@ def test_device_threshold_matches_numpy_on_a_stream():
         a, b = dev.demodulate(), host.demodulate()
         if c > 0:
             np.testing.assert_array_equal(a[0], b[0])
-            np.testing.assert_array_equal(a[2], b[2])
+            # (the trust bytes are the low mantissa bytes of the float magnitudes, dem_base:1005-1007: they follow the
+            #  1e-6 differences of the clipped samples and are compared in the exact-magnitude test above instead)
         clipped += len(dev.clippedPeakIPure)
         ra[:ovl] = ra[-ovl:]
         rb[:ovl] = rb[-ovl:]
