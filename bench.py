@@ -381,6 +381,9 @@ def main():
                     help="256-point search: 0 shifted filters (default), 1 / 2 rotate-the-chunk comparison variants")
     ap.add_argument("--items-per-cta", type=int, default=0, help="tuning knob of the shifted-filter search kernel")
     ap.add_argument("--warps20", action="store_true", help="tuning knob: 96-register build of the shifted-filter kernel")
+    ap.add_argument("--doppler-bins", type=int, default=0,
+                    help="experiment: override doppCarrierSteps (e.g. one rank's slice of the bins on a single GPU); the "
+                         "line then no longer measures the named workload and says so")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the per-rank Doppler-bin tables reach the estimate (NVLink peer stores | NCCL all-gather)")
     ap.add_argument("--inflight", type=int, default=0,
@@ -394,6 +397,9 @@ def main():
     from pycusdr_b200.config import loadModularJson
     cfg_file, modulation, desc = WORKLOADS[args.workload]
     conf = loadModularJson(os.path.join(ROOT, "config", cfg_file))
+    if args.doppler_bins:
+        conf["Radios"]["Rx"][RADIO]["doppCarrierSteps"] = args.doppler_bins
+        desc += f" [EXPERIMENT: {args.doppler_bins} Doppler bins]"
     if args.impl == "reference":
         return run_reference(args, conf, desc)
 

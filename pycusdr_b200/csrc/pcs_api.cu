@@ -710,9 +710,11 @@ static int enqueue_search_local256(pcs_handle* h) {
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
         // items per CTA: 64 amortises the per-CTA set-up (twiddles, the bin's 2 KB x M filter spectra); small searches
-        // (short chunks, a rank's slice of the bins) get smaller CTAs so that the grid still covers >= 4 waves
+        // (short chunks, a rank's slice of the bins) get smaller CTAs so that the grid still covers >= 2 waves of 4 CTAs
+        // per SM (measured on 32- and 128-bin slices of C2: with chunks in flight 64 beats 8-32 by 3-7 %, for a single
+        // chunk in flight 16-32 is 10 % quicker on the 32-bin slice)
         q.items_per_cta = h->fs_items > 0 ? h->fs_items
-                                          : (int)std::min<long long>(64, std::max<long long>(G, items / (16LL * h->sm_count) / G * G));
+                                          : (int)std::min<long long>(64, std::max<long long>(G, items / (8LL * h->sm_count) / G * G));
         h->search_ctas = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
         const size_t dyn = (size_t)p.M * 128 * sizeof(float4) + (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + dyn);
