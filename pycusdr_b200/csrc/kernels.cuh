@@ -52,6 +52,9 @@ struct OsSearchParams {
     int* __restrict__ pidx;             // [D][M][nblk]
     int N, D, M, nblk, V, Lpos;
     float invN;
+    // shifted-filter form (FS = true): block spectra of the unrotated chunk and per-bin filter spectra
+    const float2* __restrict__ xbs;     // [nblk][B]
+    const float2* __restrict__ gs;      // [D][M][B] = Mk[m][(k N/B - s_d) % N] * N/B
 };
 
 struct PeakAcc {
@@ -100,30 +103,33 @@ struct RotatePre {
     }
 };
 
-template <int LOGB, int G>
+// FS = true: the shifted-filter form (see search_fs256_kernel): no rotation and no forward transform per item; the
+// block spectrum comes from block_spectra_kernel's table and the filter spectra are the bin's own.  Items are then
+// ordered block-fastest so that the groups of a CTA share the bin's filter spectra in L1.
+template <int LOGB, int G, bool FS>
 __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSearchParams p) {
     using S = FftShape<LOGB>;
-    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32;
+    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32, NBUF = 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    float2* xb = smem + (size_t)g * 3 * S::WORK;
-    float2* work0 = xb + S::WORK;
+    float2* work0 = smem + (size_t)g * NBUF * S::WORK;
     float2* work1 = work0 + S::WORK;
+    float2* xb = work1 + S::WORK;       // the item's block spectrum
     // per-group reduction scratch behind the FFT buffers: [G][M][NW] x {sum, max, idx}
-    float* red = reinterpret_cast<float*>(smem + (size_t)G * 3 * S::WORK) + (size_t)g * p.M * NW * 3;
+    float* red = reinterpret_cast<float*>(smem + (size_t)G * NBUF * S::WORK) + (size_t)g * p.M * NW * 3;
     const int bar_id = 1 + g;
 
     const long long item = (long long)blockIdx.x * G + g;
     if (item >= (long long)p.nblk * p.D) return;      // whole group leaves (own barrier id)
-    const int blk = (int)(item / p.D), d = (int)(item % p.D);
+    const int blk = FS ? (int)(item % p.nblk) : (int)(item / p.D), d = FS ? (int)(item / p.nblk) : (int)(item % p.D);
     const uint32_t nmask = (uint32_t)p.N - 1u;
-    const uint32_t shift = (uint32_t)p.shifts[d];
     const int n0 = blk * p.V;
-    const uint32_t n_first = (uint32_t)(n0 - p.Lpos) & nmask;
 
     // ---- forward transform of the rotated block -> xb (natural order) ----
-    {
+    if (!FS) {
+        const uint32_t shift = (uint32_t)p.shifts[d];
+        const uint32_t n_first = (uint32_t)(n0 - p.Lpos) & nmask;
         RotatePre pre;
         pre.shift = shift;
         pre.n_first = n_first;
@@ -133,13 +139,17 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSear
         auto src = [&](int i) { return __ldg(&p.x[(n_first + (uint32_t)i) & nmask]); };
         auto sink = [&](int i, float2 v, int) { xb[padi(i)] = v; };
         group_fft<LOGB, -1>(work0, work1, p.tw, t, bar_id, src, sink, pre);
+    } else {
+        const float2* __restrict__ xs = p.xbs + (size_t)blk * B;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xb[padi(t + r * T)] = __ldg(&xs[t + r * T]);
     }
     group_sync<T>(bar_id);
 
     const int vlen = min(p.V, p.N - n0);
     const int lane = t & 31, warp = t >> 5;
     for (int m = 0; m < p.M; ++m) {
-        const float2* __restrict__ gm = p.gb + (size_t)m * B;
+        const float2* __restrict__ gm = FS ? p.gs + ((size_t)d * p.M + m) * B : p.gb + (size_t)m * B;
         PeakAcc acc;
         acc.init();
         auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
@@ -171,6 +181,41 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSear
         p.pmax[o] = acc.best;
         p.pidx[o] = acc.idx;
     }
+}
+
+// Block spectra of the unrotated chunk for the shifted-filter form of the generic kernel: one group per block.
+template <int LOGB, int G>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T) block_spectra_kernel(const float2* __restrict__ x,
+                                                                               const float2* __restrict__ tw,
+                                                                               float2* __restrict__ xbs, int N, int nblk, int V,
+                                                                               int Lpos) {
+    using S = FftShape<LOGB>;
+    constexpr int B = S::B, T = S::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* smem = reinterpret_cast<float2*>(smem_raw);
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    float2* work0 = smem + (size_t)g * 2 * S::WORK;
+    float2* work1 = work0 + S::WORK;
+    const int blk = blockIdx.x * G + g;
+    if (blk >= nblk) return;
+    const uint32_t nmask = (uint32_t)N - 1u, n_first = (uint32_t)(blk * V - Lpos) & nmask;
+    float2* __restrict__ out = xbs + (size_t)blk * B;
+    auto src = [&](int i) { return __ldg(&x[(n_first + (uint32_t)i) & nmask]); };
+    auto sink = [&](int i, float2 v, int) { out[i] = v; };
+    group_fft<LOGB, -1>(work0, work1, tw, t, 1 + g, src, sink);
+}
+
+// G[d][m][k] = Mk[m][(k N/B - s_d) % N] * N/B, natural order (once per handle).
+__global__ void shifted_filters_kernel(const float2* __restrict__ masks, const int* __restrict__ shifts,
+                                       float2* __restrict__ gs, int N, int logB, int D, int M) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ((long long)D * M) << logB) return;
+    const int k = (int)(idx & ((1 << logB) - 1));
+    const int dm = (int)(idx >> logB), m = dm % M, d = dm / M;
+    const uint32_t nmask = (uint32_t)N - 1u, dec = (uint32_t)(N >> logB);
+    const float scale = (float)dec;
+    const float2 a = masks[(size_t)m * N + (((uint32_t)k * dec - (uint32_t)shifts[d]) & nmask)];
+    gs[idx] = make_float2(a.x * scale, a.y * scale);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -90,6 +90,7 @@ struct pcs_handle {
     unsigned int *d_thr_bits = nullptr, *h_thr_bits = nullptr;
     bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
     float4 *d_xbs = nullptr, *d_gs = nullptr;
+    float2 *d_xbs_os = nullptr, *d_gs_os = nullptr;    // the same for the generic kernel (natural order)
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
     int* d_part_blk = nullptr;
@@ -272,16 +273,28 @@ static int fft_large(pcs_handle* h, Load ld, float2* out) {
 }
 
 // ---- overlap-save launchers ---------------------------------------------------------------------
-template <int LOGB, int G>
+template <int LOGB, int G, bool FS>
 static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p) {
     using S = FftShape<LOGB>;
-    constexpr int NW = (S::T + 31) / 32;
-    const size_t smem = (size_t)G * 3 * S::WORK * sizeof(float2) + (size_t)G * p.M * NW * 3 * sizeof(float);
-    auto kern = search_os_kernel<LOGB, G>;
+    constexpr int NW = (S::T + 31) / 32, NBUF = 3;
+    const size_t smem = (size_t)G * NBUF * S::WORK * sizeof(float2) + (size_t)G * p.M * NW * 3 * sizeof(float);
+    auto kern = search_os_kernel<LOGB, G, FS>;
     static size_t configured[PCS_MAX_DEVICES] = {};
     if (configured[h->cfg.device] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device] = smem;
+    }
+    if (FS) {      // block spectra of the unrotated chunk, once per chunk
+        const size_t bs_smem = (size_t)G * 2 * S::WORK * sizeof(float2);
+        auto bs = block_spectra_kernel<LOGB, G>;
+        static size_t bs_configured[PCS_MAX_DEVICES] = {};
+        if (bs_configured[h->cfg.device] < bs_smem) {
+            CUDA_TRY(cudaFuncSetAttribute(bs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
+            bs_configured[h->cfg.device] = bs_smem;
+        }
+        bs<<<(p.nblk + G - 1) / G, G * S::T, bs_smem, h->stream>>>(p.x, p.tw, h->d_xbs_os, p.N, p.nblk, p.V, p.Lpos);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
     }
     const long long items = (long long)p.nblk * p.D;
     const int grid = (int)((items + G - 1) / G);
@@ -312,11 +325,11 @@ static int launch_demod_os_t(pcs_handle* h, const OsDemodParams& p) {
 
 static int launch_search_os(pcs_handle* h, const OsSearchParams& p) {
     switch (h->logB) {
-        case 9: return launch_search_os_t<9, 8>(h, p);
-        case 10: return launch_search_os_t<10, 4>(h, p);
-        case 11: return launch_search_os_t<11, 2>(h, p);
-        case 12: return launch_search_os_t<12, 1>(h, p);
-        case 13: return launch_search_os_t<13, 1>(h, p);
+        case 9: return p.xbs ? launch_search_os_t<9, 8, true>(h, p) : launch_search_os_t<9, 8, false>(h, p);
+        case 10: return p.xbs ? launch_search_os_t<10, 4, true>(h, p) : launch_search_os_t<10, 4, false>(h, p);
+        case 11: return p.xbs ? launch_search_os_t<11, 2, true>(h, p) : launch_search_os_t<11, 2, false>(h, p);
+        case 12: return p.xbs ? launch_search_os_t<12, 1, true>(h, p) : launch_search_os_t<12, 1, false>(h, p);
+        case 13: return p.xbs ? launch_search_os_t<13, 1, true>(h, p) : launch_search_os_t<13, 1, false>(h, p);
     }
     return fail(PCS_ERR_INVALID, "unsupported overlap-save block 2^%d", h->logB);
 }
@@ -395,6 +408,19 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_psum, np)) return rc;
     if (int rc = dev_alloc(h, &h->d_pmax, np)) return rc;
     if (int rc = dev_alloc(h, &h->d_pidx, np)) return rc;
+    // Shifted-filter form (see plan_fast256) for the generic kernel, when the 256-point plan will not take the search
+    // and the per-bin spectra stay modest (D * M * B * 8 bytes: 8 MiB for CC11xx); reserved[2] != 0 keeps the rotate form.
+    const int L256 = 256 - L + 1;
+    const bool fast256_will_run = (h->cfg.log2_block == 0 || h->cfg.log2_block == 8) && L256 >= 128 && N >= 4096;
+    const size_t gs_elems = (size_t)h->D * M * B;
+    if (h->cfg.reserved[2] == 0 && !fast256_will_run && gs_elems * sizeof(float2) <= ((size_t)256 << 20)) {
+        if (int rc = dev_alloc(h, &h->d_xbs_os, (size_t)h->nblk * B)) return rc;
+        if (int rc = dev_alloc(h, &h->d_gs_os, gs_elems)) return rc;
+        shifted_filters_kernel<<<(unsigned)((gs_elems + 255) / 256), 256, 0, h->stream>>>(h->d_masks, h->d_shifts, h->d_gs_os, N,
+                                                                                          best, h->D, M);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 
@@ -809,6 +835,8 @@ static int enqueue_search_local(pcs_handle* h) {
     const size_t row0 = (size_t)h->bin_lo * h->M;
     OsSearchParams p{};
     p.x = h->d_x_cur; p.gb = h->d_gb; p.shifts = h->d_shifts + h->bin_lo;
+    p.xbs = h->d_xbs_os;
+    p.gs = h->d_gs_os ? h->d_gs_os + ((size_t)row0 << h->logB) : nullptr;
     p.psum = h->d_psum + row0 * h->nblk; p.pmax = h->d_pmax + row0 * h->nblk; p.pidx = h->d_pidx + row0 * h->nblk;
     p.N = h->N; p.D = Dl; p.M = h->M; p.nblk = h->nblk; p.V = h->V; p.Lpos = h->Lpos;
     p.invN = 1.0f / (float)h->N;

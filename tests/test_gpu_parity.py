@@ -253,10 +253,31 @@ def test_search_forms_agree(kw):
     assert rel_err(Eb, Eo) < 1e-4 and rel_err(vb, pv) < 1e-4
 
 
-def test_search_bin_range_rows_equal_the_full_table():
+@pytest.mark.parametrize("log2_block", [9, 11])
+def test_generic_kernel_forms_agree(log2_block):
+    """Shifted-filter and rotate-the-chunk forms of the generic (shared-memory) search kernel: same numbers to fp32 rounding."""
+    conf = conf_variant("benchmark/bench_GMSK.json", blockSize=14, doppCarrierSteps=24, noise_measure_offset_Hz=30000)
+    demA, orc = _demods(conf, fused=False, log2_block=log2_block)
+    demB, _ = _demods(conf, fused=False, log2_block=log2_block, search_form=2)
+    x = _noise_chunk(2 ** 14, 13, with_packet="GMSK")
+    out = []
+    for dem in (demA, demB):
+        dem.get_signalBufferHostPointer()[:] = x
+        dem.uploadToGPU(dem.get_signalBufferHostPointer())
+        res, E = dem._engine.search()
+        v, o = dem._engine.peaks()
+        out.append((res, E.copy(), v.copy(), o.copy()))
+    (ra, Ea, va, oa), (rb, Eb, vb, ob) = out
+    assert demA._engine.launch_count == demB._engine.launch_count + 1        # the block-spectra kernel
+    assert rel_err(Ea, Eb) < 2e-6 and rel_err(va, vb) < 2e-6 and np.mean(oa != ob) <= 0.02
+    assert (ra.shift, ra.low_idx, ra.high_idx) == (rb.shift, rb.low_idx, rb.high_idx)
+
+
+@pytest.mark.parametrize("log2_block", [0, 10])
+def test_search_bin_range_rows_equal_the_full_table(log2_block):
     """Bin sharding: rows [lo, hi) searched on their own are bit-identical to the same rows of the full search."""
     conf = conf_variant("benchmark/bench_GMSK.json", blockSize=14, doppCarrierSteps=24)
-    dem, _ = _demods(conf, fused=False)
+    dem, _ = _demods(conf, fused=False, log2_block=log2_block)
     eng = dem._engine
     x = _noise_chunk(2 ** 14, 12, with_packet="GMSK")
     import torch
