@@ -693,6 +693,56 @@ def main():
                "bits_per_step": nbits / e2e_steps,
                "api": "demodulator.UHF.Demodulator.uploadAndFindCarrier + demodulate (pinned chunk buffer)"}
 
+    # ---- e2e at N > 1: host samples on every rank -> pinned buffer -> H2D -> sharded search -> owner tail -> owner D2H
+    # + bit post-processing on the owner.  Every rank ingests the whole chunk ("one H2D per GPU"). ----
+    if sh is not None:
+        e2e_n = min(args.steps, 200) // (world * K) * (world * K) or world * K
+        blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
+        dems = [dem] + extra
+        bufs = [d.get_signalBufferHostPointer() for d in dems]
+        for b in bufs:
+            b[:] = 0
+        nbits = [0]
+
+        def to_bits(pipe):
+            def f(out):
+                r, _, sym, centre, mag = out
+                bits, _, _ = dems[pipe]._stitch(sym, centre, mag, (), np.float64(r.sp_sym))
+                nbits[0] += len(bits)
+                return len(bits)
+            return f
+
+        def run(first, count):
+            for i in range(first, first + count):
+                pipe = i % K
+                streams[pipe].synchronize()           # the pipeline's previous H2D has left the pinned buffer
+                raw = bufs[pipe]
+                raw[:ovl] = bufs[(i - 1) % K][-ovl:]   # overlap carry (demodulator_process.py:337)
+                raw[ovl:] = blocks[i % ring]
+                sh.pipes[pipe].enqueue(sh.pipes[pipe].next_seq, None, collect=to_bits(pipe))
+            for j, p in enumerate(sh.pipes):
+                p.drain(to_bits(j))
+        base = 0
+        run(base, world * K)                          # warm-up round of the host path
+        torch.cuda.synchronize()
+        dist.barrier()
+        nbits[0] = 0
+        t0 = time.perf_counter()
+        run(base + world * K, e2e_n)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nb = torch.tensor([nbits[0]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(nb)
+        dt = float(dt.item())
+        e2e = {"value": step_samples * e2e_n / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * world,
+               "d2h_bytes_per_step": int(88 + 4 * D * M + 12 * eng.max_sym), "steps": e2e_n, "ms_per_step": dt / e2e_n * 1e3,
+               "bits_per_step": int(nb.item()) / e2e_n,
+               "api": "sharded.ShardedPipelines.enqueue(chunk=None) on every rank: samples in each rank's pinned buffer, "
+                      "H2D + bin-sharded search on all ranks, tail + D2H + bit post-processing on the chunk's owner",
+               "note": "max over ranks of the wall time between barriers; the +-1-bit realignment between consecutive chunks "
+                       "(checkSymbolOverlap) is evaluated against the owner's previous chunk, not the stream's"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

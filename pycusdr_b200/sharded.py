@@ -53,8 +53,10 @@ class ShardedSearch:
         self.results = {}              # seq -> whatever ``collect`` made of engine.fetch()
         self._next_seq = 0
 
-    def enqueue(self, seq, chunk, collect=None):
-        """Enqueue chunk ``seq`` (device pointer / array understood by the engine). Chunks must come in order.
+    def enqueue(self, seq, chunk=None, collect=None):
+        """Enqueue chunk ``seq``. ``chunk`` is a device pointer / array understood by the engine, or ``None`` when the
+        samples have been written into the engine's pinned host buffer (``engine.host_buffer``): the H2D copy is then
+        part of the enqueued work, as in ``uploadToGPU`` (dem_base:548-558).  Chunks must come in order.
         If this rank owns the chunk its tail is enqueued too; the results of the previously owned chunk are collected
         first (the engine has one result staging area), through ``collect(fetch_tuple)`` if given."""
         if seq != self._next_seq:
@@ -63,12 +65,20 @@ class ShardedSearch:
         owner = owner_of(seq, self.world)
         if owner == self.rank:
             self.drain(collect)
-        self.engine.upload_device(chunk)
+        if chunk is None:
+            self.engine.upload()
+        else:
+            self.engine.upload_device(chunk)
         self.engine.enqueue_search_push(seq, owner)
         if owner == self.rank:
             self.engine.enqueue_owner_tail(seq)
             self._owned.append(seq)
         return owner
+
+    @property
+    def next_seq(self):
+        """Sequence number the next ``enqueue`` must carry."""
+        return self._next_seq
 
     def drain(self, collect=None):
         """Collect the results of every owned chunk still in flight (synchronises with the device)."""
@@ -94,7 +104,7 @@ class ShardedPipelines:
         self.rank, self.world = rank, world
         self.slices = self.pipes[0].slices
 
-    def enqueue(self, chunk_no, chunk, collect=None):
+    def enqueue(self, chunk_no, chunk=None, collect=None):
         P = len(self.pipes)
         return self.pipes[chunk_no % P].enqueue(chunk_no // P, chunk, collect)
 

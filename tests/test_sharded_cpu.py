@@ -64,6 +64,7 @@ class FakeEngine:
         self.tables = {}
         self.out = None
         self.log = []
+        self.host_buffer = np.zeros(4096, np.complex64)      # stand-in for the pinned chunk buffer
 
     def set_bin_range(self, lo, hi):
         self.lo, self.hi = lo, hi
@@ -77,6 +78,9 @@ class FakeEngine:
 
     def upload_device(self, chunk):
         self.x = chunk
+
+    def upload(self):                       # chunk=None: the samples sit in the engine's pinned host buffer
+        self.x = self.host_buffer.copy()
 
     def _rows(self):
         X = O.forward_fft(self.x)
@@ -130,7 +134,13 @@ def _worker(rank, world, port, q, pipes=1):
         else:
             sh = sharded.ShardedPipelines([FakeEngine(rank, world, j) for j in range(pipes)], rank, world, all_gather)
             want_owner = [(s // pipes) % world for s in range(N_CHUNKS)]
-        owners = [sh.enqueue(seq, x) for seq, x in enumerate(_chunks())]
+        if pipes == 1:
+            owners = [sh.enqueue(seq, x) for seq, x in enumerate(_chunks())]
+        else:                               # host-buffer ingestion: samples written into the pipeline's pinned buffer
+            owners = []
+            for seq, x in enumerate(_chunks()):
+                sh.pipes[seq % pipes].engine.host_buffer[:] = x
+                owners.append(sh.enqueue(seq))
         sh.drain()
         assert owners == want_owner
         assert sorted(sh.results) == [s for s in range(N_CHUNKS) if want_owner[s] == rank]
