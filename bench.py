@@ -694,20 +694,41 @@ def main():
                "api": "demodulator.UHF.Demodulator.uploadAndFindCarrier + demodulate (pinned chunk buffer)"}
 
     # ---- e2e at N > 1: host samples on every rank -> pinned buffer -> H2D -> sharded search -> owner tail -> owner D2H
-    # + bit post-processing on the owner.  Every rank ingests the whole chunk ("one H2D per GPU"). ----
+    # + bit post-processing on the owner, with the chunk-to-chunk carry of checkSymbolOverlap passed from owner to owner
+    # (sharded.OrderedStitcher) so that the bit stream is the one a single process produces.  Every rank ingests the whole
+    # chunk ("one H2D per GPU"). ----
     if sh is not None:
+        from collections import deque
         e2e_n = min(args.steps, 200) // (world * K) * (world * K) or world * K
         blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
         dems = [dem] + extra
         bufs = [d.get_signalBufferHostPointer() for d in dems]
         for b in bufs:
             b[:] = 0
+        gloo = dist.new_group(backend="gloo")
+        seq0 = [p.next_seq for p in sh.pipes]
+
+        def owner_of_chunk(c):
+            return sharded.owner_of(seq0[c % K] + c // K, world)
+        sends = []
+
+        def send(token, dst, c):
+            buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+            sends.append(dist.isend(buf, dst=dst, tag=c, group=gloo))
+
+        def recv(src, c):
+            buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            dist.recv(buf, src=src, tag=c, group=gloo)
+            return buf.numpy().tobytes()
+        ordered = sharded.OrderedStitcher(dem._stitch, rank, owner_of_chunk, send, recv)
+        owned = [deque() for _ in range(K)]
         nbits = [0]
 
         def to_bits(pipe):
             def f(out):
                 r, _, sym, centre, mag = out
-                bits, _, _ = dems[pipe]._stitch(sym, centre, mag, (), np.float64(r.sp_sym))
+                bits, _, _ = ordered(owned[pipe].popleft(), sym, centre, mag, (), np.float64(r.sp_sym))
                 nbits[0] += len(bits)
                 return len(bits)
             return f
@@ -719,29 +740,35 @@ def main():
                 raw = bufs[pipe]
                 raw[:ovl] = bufs[(i - 1) % K][-ovl:]   # overlap carry (demodulator_process.py:337)
                 raw[ovl:] = blocks[i % ring]
+                if owner_of_chunk(i) == rank:
+                    owned[pipe].append(i)
                 sh.pipes[pipe].enqueue(sh.pipes[pipe].next_seq, None, collect=to_bits(pipe))
             for j, p in enumerate(sh.pipes):
                 p.drain(to_bits(j))
-        base = 0
-        run(base, world * K)                          # warm-up round of the host path
+        run(0, world * K)                             # warm-up round of the host path
         torch.cuda.synchronize()
         dist.barrier()
         nbits[0] = 0
         t0 = time.perf_counter()
-        run(base + world * K, e2e_n)
+        run(world * K, e2e_n)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        last = world * K + e2e_n - 1                  # its carry is addressed to the owner of a chunk that never comes
+        if owner_of_chunk(last + 1) == rank and owner_of_chunk(last) != rank:
+            recv(owner_of_chunk(last), last)
+        for w in sends:
+            w.wait()
         nb = torch.tensor([nbits[0]], device="cuda", dtype=torch.int64)
         dist.all_reduce(nb)
         dt = float(dt.item())
         e2e = {"value": step_samples * e2e_n / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * world,
                "d2h_bytes_per_step": int(88 + 4 * D * M + 12 * eng.max_sym), "steps": e2e_n, "ms_per_step": dt / e2e_n * 1e3,
                "bits_per_step": int(nb.item()) / e2e_n,
-               "api": "sharded.ShardedPipelines.enqueue(chunk=None) on every rank: samples in each rank's pinned buffer, "
-                      "H2D + bin-sharded search on all ranks, tail + D2H + bit post-processing on the chunk's owner",
-               "note": "max over ranks of the wall time between barriers; the +-1-bit realignment between consecutive chunks "
-                       "(checkSymbolOverlap) is evaluated against the owner's previous chunk, not the stream's"}
+               "api": "sharded.ShardedPipelines.enqueue(chunk=None) on every rank (samples in each rank's pinned buffer, H2D + "
+                      "bin-sharded search on all ranks, tail + D2H on the chunk's owner) + sharded.OrderedStitcher (bit "
+                      "post-processing on the owner, chunk-to-chunk carry passed owner to owner over gloo)",
+               "note": "max over ranks of the wall time between barriers"}
 
     if rank != 0:
         if dist is not None:

@@ -236,6 +236,12 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
                      uint8_t* trust_out, int32_t* n_out);
 int pcs_stitch_reset(pcs_stitcher* s);
 int pcs_stitch_destroy(pcs_stitcher* s);
+/* The carry between consecutive chunks (poswinP, posSymEnd of dem_base:977-979) as bytes: n_poswin bits followed by
+ * n_posend bits.  It depends on its own chunk's symbols only, so a host that post-processes consecutive chunks in
+ * different processes (bin sharding: the owner of a chunk rotates over the ranks) passes it from the owner of chunk k to
+ * the owner of chunk k + 1 and gets exactly the bit stream a single process produces. */
+int pcs_stitch_get_state(const pcs_stitcher* s, uint8_t* buf, int32_t cap, int32_t* n_poswin, int32_t* n_posend);
+int pcs_stitch_set_state(pcs_stitcher* s, const uint8_t* buf, int32_t n_poswin, int32_t n_posend);
 
 /* computeSNR's two window means (dem_base:657-663): mean |X| over the signal and the noise window gathered by the last
  * search, when the windows do not touch the ends of the spectrum (*ok = 1); otherwise *ok = 0 and the caller applies the

@@ -85,6 +85,8 @@ SYMBOLS = {
     "pcs_stitch_create": (C.c_int, [C.POINTER(StitchConfig), _P, _P, C.POINTER(_P)]),
     "pcs_stitch_chunk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_stitch_reset": (C.c_int, [_P]),
+    "pcs_stitch_get_state": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pcs_stitch_set_state": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     "pcs_stitch_destroy": (C.c_int, [_P]),
     "pcs_ingest_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "pcs_ingest_push": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
@@ -206,6 +208,24 @@ class Stitcher:
 
     def reset(self):
         self.lib.pcs_stitch_reset(self._h)
+
+    STATE_BYTES = 1024
+
+    def get_state(self):
+        """The carry to the next chunk as ``bytes``: 2-byte counts (poswinP, posSymEnd) + the bits themselves."""
+        buf = np.empty(self.STATE_BYTES, dtype=np.uint8)
+        a, b = C.c_int32(0), C.c_int32(0)
+        rc = self.lib.pcs_stitch_get_state(self._h, _ptr(buf), self.STATE_BYTES - 4, C.byref(a), C.byref(b))
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+        return int(a.value).to_bytes(2, "little") + int(b.value).to_bytes(2, "little") + buf[:a.value + b.value].tobytes()
+
+    def set_state(self, token):
+        a, b = int.from_bytes(token[:2], "little"), int.from_bytes(token[2:4], "little")
+        buf = np.frombuffer(token, dtype=np.uint8, count=a + b, offset=4).copy() if a + b else np.empty(0, np.uint8)
+        rc = self.lib.pcs_stitch_set_state(self._h, _ptr(buf) if a + b else None, a, b)
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
 
     def close(self):
         h = getattr(self, "_h", None)

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -79,6 +80,28 @@ int pcs_stitch_reset(pcs_stitcher* s) {
 
 int pcs_stitch_destroy(pcs_stitcher* s) {
     delete s;
+    return PCS_OK;
+}
+
+// The carry between consecutive chunks (dem_base:977-979: poswinP = the bits behind the window, posSymEnd = the last
+// overlap_offset + 1 bits of the window).  It is a function of its own chunk's symbols alone, which is what lets chunks be
+// post-processed on different ranks: the owner of chunk k hands this to the owner of chunk k + 1.
+int pcs_stitch_get_state(const pcs_stitcher* s, uint8_t* buf, int32_t cap, int32_t* n_poswin, int32_t* n_posend) {
+    if (!s || !n_poswin || !n_posend) return pcs_fail_msg(PCS_ERR_INVALID, "null argument");
+    const size_t a = s->poswinP.size(), b = s->posSymEnd.size();
+    *n_poswin = (int32_t)a;
+    *n_posend = (int32_t)b;
+    if (a + b > (size_t)std::max(cap, 0) || (a + b > 0 && !buf)) return pcs_fail_msg(PCS_ERR_INVALID, "state buffer too small");
+    if (a) memcpy(buf, s->poswinP.data(), a);
+    if (b) memcpy(buf + a, s->posSymEnd.data(), b);
+    return PCS_OK;
+}
+
+int pcs_stitch_set_state(pcs_stitcher* s, const uint8_t* buf, int32_t n_poswin, int32_t n_posend) {
+    if (!s || n_poswin < 0 || n_posend < 0 || (n_poswin + n_posend > 0 && !buf)) return pcs_fail_msg(PCS_ERR_INVALID, "bad argument");
+    s->poswinP.assign(buf, buf + n_poswin);
+    s->posSymEnd.assign(buf + n_poswin, buf + n_poswin + n_posend);
+    s->have_prev = n_poswin > 0;
     return PCS_OK;
 }
 

@@ -120,6 +120,54 @@ class ShardedPipelines:
         return {q * P + j: r for j, p in enumerate(self.pipes) for q, r in p.results.items()}
 
 
+class OrderedStitcher:
+    """Exact bit post-processing of a stream whose chunks are finished on different ranks.
+
+    ``checkSymbolOverlap`` (dem_base:863-988) realigns a chunk by one bit against the carry of the chunk before it
+    (``poswinP`` / ``posSymEnd``, dem_base:977-979).  That carry is a function of the earlier chunk's own symbols only,
+    so the owner of chunk ``c`` can produce it without knowing anything about chunk ``c - 1``: it post-processes its
+    chunk once to obtain the carry and sends it to the owner of chunk ``c + 1`` straight away, then takes the carry of
+    chunk ``c - 1`` from that chunk's owner and post-processes again, now with the right alignment.  The bits that come
+    out are exactly what one process stitching every chunk in order produces; no rank ever waits on a chain longer than
+    one message.  When a rank owns consecutive chunks the carry is already in place and one pass is enough.
+
+    ``stitcher`` has the interface of ``_native.Stitcher`` (``__call__``, ``get_state``, ``set_state``, ``reset``);
+    ``owner_of_chunk(c)`` gives the rank that finishes global chunk ``c``; ``send(token, dst, c)`` and
+    ``recv(src, c)`` move the carry of chunk ``c`` (``bytes``) between ranks (e.g. ``torch.distributed`` point-to-point
+    on a ``gloo`` group)."""
+
+    def __init__(self, stitcher, rank, owner_of_chunk, send, recv):
+        self.stitcher, self.rank, self.owner_of_chunk = stitcher, rank, owner_of_chunk
+        self.send, self.recv = send, recv
+        self._last = None            # chunk whose carry the stitcher currently holds
+        self._local = {}             # carries of chunks this rank owns whose successor it owns too
+        stitcher.reset()
+
+    def __call__(self, c, sym, centre, mag, clipped, sp_sym):
+        if self.owner_of_chunk(c) != self.rank:
+            raise ValueError(f"chunk {c} belongs to rank {self.owner_of_chunk(c)}")
+        st = self.stitcher
+        if c > 0 and self._last != c - 1 and self.owner_of_chunk(c - 1) == self.rank:
+            st.set_state(self._local.pop(c - 1))
+            self._last = c - 1
+        in_place = c == 0 or self._last == c - 1
+        if c == 0:
+            st.reset()
+        out = st(sym, centre, mag, clipped, sp_sym)          # exact if the right carry was in place; it is the carry pass otherwise
+        token = st.get_state()
+        nxt = self.owner_of_chunk(c + 1)
+        if nxt == self.rank:
+            self._local[c] = token
+        else:
+            self.send(token, nxt, c)
+        if not in_place:
+            st.set_state(self.recv(self.owner_of_chunk(c - 1), c - 1))
+            out = st(sym, centre, mag, clipped, sp_sym)
+        self._last = c
+        self._local.pop(c - 2, None)
+        return out
+
+
 def gather_results(results, world, gather_object, rank):
     """Merge the per-rank ``{seq: result}`` dicts on rank 0, ordered by chunk. ``gather_object(obj)`` returns the
     list of all ranks' objects on rank 0 (``None`` elsewhere)."""

@@ -1,0 +1,141 @@
+"""Exact bit post-processing when consecutive chunks are finished on different ranks (bin sharding):
+two ``gloo`` ranks run ``sharded.OrderedStitcher`` over the native stitcher and pass the chunk-to-chunk carry
+(dem_base:977-979) point to point; the merged stream must equal what ONE stitcher produces going through the chunks in
+order (which tests/test_native_stitch.py pins to the reference's own checkSymbolOverlap).  Host logic only: no GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pycusdr_b200 import _native, sharded                           # noqa: E402
+
+N, OVL, SPS, N_CHUNKS = 4096, 1024, 16, 20
+
+
+def _stitcher():
+    return _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=20, error_threshold=1000, match_threshold=10,
+                            bit_lut=np.array([0, 1], np.uint8), symbol_lut=None)
+
+
+def _chunks():
+    """Symbol tables of consecutive chunks cut from one random bit stream; a per-chunk timing jitter moves the symbols
+    next to the window edges in and out of the window, which is what the +-1-bit realignment exists for."""
+    rng = np.random.RandomState(7)
+    step = N - OVL
+    stream = rng.randint(0, 2, size=(N_CHUNKS + 2) * N // SPS).astype(np.int32)
+    out = []
+    for c in range(N_CHUNKS):
+        jitter = int(rng.randint(-14, 15))
+        k = np.arange(len(stream))
+        centre = k * SPS + 8 - c * step + jitter
+        keep = (centre >= 0) & (centre < N)
+        sym = stream[keep].copy()
+        flips = rng.rand(len(sym)) < 0.01                  # a few symbol errors
+        sym[flips] ^= 1
+        mag = rng.rand(len(sym)).astype(np.float32) * 1e3
+        clipped = np.array([700 + 13 * c, 2000], np.int64) if c % 3 == 0 else np.zeros(0, np.int64)
+        out.append((sym, centre[keep].astype(np.int32), mag, clipped, np.float64(SPS)))
+    return out
+
+
+def _sequential():
+    st = _stitcher()
+    return [st(*args) for args in _chunks()]
+
+
+def _worker(rank, world, port, q, pipes):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        owner = lambda c: (c // pipes) % world               # noqa: E731  (ShardedPipelines' schedule)
+        pending = []
+
+        def send(token, dst, c):
+            buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+            pending.append(dist.isend(buf, dst=dst, tag=c))
+
+        def recv(src, c):
+            buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            dist.recv(buf, src=src, tag=c)
+            return buf.numpy().tobytes()
+
+        os_ = sharded.OrderedStitcher(_stitcher(), rank, owner, send, recv)
+        mine = {c: os_(c, *args) for c, args in enumerate(_chunks()) if owner(c) == rank}
+        # the carry of the last chunk is addressed to the owner of a chunk that never comes: take it off the wire
+        if owner(N_CHUNKS) == rank and owner(N_CHUNKS - 1) != rank:
+            assert len(recv(owner(N_CHUNKS - 1), N_CHUNKS - 1)) == _native.Stitcher.STATE_BYTES
+        for w in pending:
+            w.wait()
+        with pytest.raises(ValueError):
+            os_(next(c for c in range(N_CHUNKS) if owner(c) != rank), *_chunks()[0])
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object({c: [a.tolist() for a in v] for c, v in mine.items()}, parts, dst=0)
+        if rank == 0:
+            merged = {}
+            for p in parts:
+                merged.update(p)
+            q.put([merged[c] for c in range(N_CHUNKS)])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_the_carry_depends_on_its_own_chunk_only():
+    """What makes the scheme possible: whatever carry a stitcher holds when it processes a chunk, the carry it holds
+    afterwards is the same."""
+    chunks = _chunks()
+    a, b = _stitcher(), _stitcher()
+    a(*chunks[0])
+    a(*chunks[1])
+    b(*chunks[5])
+    b(*chunks[1])
+    assert a.get_state() == b.get_state() and len(a.get_state()) > 4 + 21
+    b.reset()
+    assert b.get_state() == b"\0\0\0\0"
+    b.set_state(a.get_state())
+    x, y = a(*chunks[2]), b(*chunks[2])
+    assert all(np.array_equal(u, v) for u, v in zip(x, y))
+
+
+def test_the_stream_needs_the_realignment():
+    seq = _sequential()
+    fresh = []
+    for args in _chunks():
+        fresh.append(_stitcher()(*args))
+    assert sum(len(s[0]) != len(f[0]) for s, f in zip(seq, fresh)) >= 2     # the carry changes some chunks by one bit
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("pipes", [1, 2])
+def test_two_gloo_ranks_produce_the_single_process_bit_stream(pipes):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, pipes)) for r in range(world)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _sequential()
+    assert len(merged) == len(want) == N_CHUNKS
+    for got, exp in zip(merged, want):
+        for g, e in zip(got, exp):
+            assert np.array_equal(np.asarray(g, dtype=np.uint8), e)
