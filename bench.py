@@ -718,10 +718,6 @@ def main():
         for b in bufs:
             b[:] = 0
         gloo = dist.new_group(backend="gloo")
-        seq0 = [p.next_seq for p in sh.pipes]
-
-        def owner_of_chunk(c):
-            return sharded.owner_of(seq0[c % K] + c // K, world)
         sends = []
 
         def send(token, dst, c):
@@ -733,42 +729,28 @@ def main():
             buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
             dist.recv(buf, src=src, tag=c, group=gloo)
             return buf.numpy().tobytes()
-        ordered = sharded.OrderedStitcher(dem._stitch, rank, owner_of_chunk, send, recv)
-        owned = [deque() for _ in range(K)]
-        nbits = [0]
+        bs = sharded.ShardedBitStream(sh, dem._stitch, rank, world, send, recv, first_chunk=sh.chunks_enqueued)
 
-        def to_bits(pipe):
-            def f(out):
-                r, _, sym, centre, mag = out
-                bits, _, _ = ordered(owned[pipe].popleft(), sym, centre, mag, (), np.float64(r.sp_sym))
-                nbits[0] += len(bits)
-                return len(bits)
-            return f
-
-        def run(first, count):
-            for i in range(first, first + count):
-                pipe = i % K
+        def run(count):
+            for _ in range(count):
+                pipe, i = bs.next_pipe, bs.next
                 streams[pipe].synchronize()           # the pipeline's previous H2D has left the pinned buffer
                 raw = bufs[pipe]
                 raw[:ovl] = bufs[(i - 1) % K][-ovl:]   # overlap carry (demodulator_process.py:337)
                 raw[ovl:] = blocks[i % ring]
-                if owner_of_chunk(i) == rank:
-                    owned[pipe].append(i)
-                sh.pipes[pipe].enqueue(sh.pipes[pipe].next_seq, None, collect=to_bits(pipe))
-            for j, p in enumerate(sh.pipes):
-                p.drain(to_bits(j))
-        run(0, world * K)                             # warm-up round of the host path
+                bs.submit()
+            bs.drain()                                # in chunk order: the carries travel from chunk to chunk
+        run((-bs.first) % (world * K) + world * K)    # warm-up: up to the next whole owner round, plus one round
         torch.cuda.synchronize()
         dist.barrier()
-        nbits[0] = 0
+        nb0 = sum(len(v[0]) for v in bs.bits.values())
         t0 = time.perf_counter()
-        run(world * K, e2e_n)
+        run(e2e_n)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        last = world * K + e2e_n - 1                  # its carry is addressed to the owner of a chunk that never comes
-        if owner_of_chunk(last + 1) == rank and owner_of_chunk(last) != rank:
-            recv(owner_of_chunk(last), last)
+        bs.finish()
+        nbits = [sum(len(v[0]) for v in bs.bits.values()) - nb0]
         for w in sends:
             w.wait()
         nb = torch.tensor([nbits[0]], device="cuda", dtype=torch.int64)

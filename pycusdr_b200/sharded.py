@@ -109,9 +109,20 @@ class ShardedPipelines:
         return self.pipes[chunk_no % P].enqueue(chunk_no // P, chunk, collect)
 
     def drain(self, collect=None):
-        for p in self.pipes:
-            p.drain(collect)
+        """Collect every owned chunk still in flight, in increasing chunk order across the pipelines (each holds at most
+        one).  The order matters to a collector that carries state from chunk to chunk across ranks (OrderedStitcher):
+        pipeline-by-pipeline draining can leave two ranks waiting for each other's carries.  ``collect`` may be one
+        callable or one per pipeline."""
+        P = len(self.pipes)
+        order = sorted((p._owned[0] * P + j, j) for j, p in enumerate(self.pipes) if p._owned)
+        for _, j in order:
+            self.pipes[j].drain(collect[j] if isinstance(collect, (list, tuple)) else collect)
         return self.results
+
+    @property
+    def chunks_enqueued(self):
+        """Number of chunks enqueued so far = the chunk number the next ``enqueue`` must carry."""
+        return sum(p.next_seq for p in self.pipes)
 
     @property
     def results(self):
@@ -136,9 +147,10 @@ class OrderedStitcher:
     ``recv(src, c)`` move the carry of chunk ``c`` (``bytes``) between ranks (e.g. ``torch.distributed`` point-to-point
     on a ``gloo`` group)."""
 
-    def __init__(self, stitcher, rank, owner_of_chunk, send, recv):
+    def __init__(self, stitcher, rank, owner_of_chunk, send, recv, first_chunk=0):
         self.stitcher, self.rank, self.owner_of_chunk = stitcher, rank, owner_of_chunk
         self.send, self.recv = send, recv
+        self.first = first_chunk     # the chunk the stream starts with: it has no carry to wait for
         self._last = None            # chunk whose carry the stitcher currently holds
         self._local = {}             # carries of chunks this rank owns whose successor it owns too
         stitcher.reset()
@@ -147,11 +159,13 @@ class OrderedStitcher:
         if self.owner_of_chunk(c) != self.rank:
             raise ValueError(f"chunk {c} belongs to rank {self.owner_of_chunk(c)}")
         st = self.stitcher
-        if c > 0 and self._last != c - 1 and self.owner_of_chunk(c - 1) == self.rank:
+        if c < self.first:
+            raise ValueError(f"chunk {c} precedes the first chunk of the stream ({self.first})")
+        if c > self.first and self._last != c - 1 and self.owner_of_chunk(c - 1) == self.rank:
             st.set_state(self._local.pop(c - 1))
             self._last = c - 1
-        in_place = c == 0 or self._last == c - 1
-        if c == 0:
+        in_place = c == self.first or self._last == c - 1
+        if c == self.first:
             st.reset()
         out = st(sym, centre, mag, clipped, sp_sym)          # exact if the right carry was in place; it is the carry pass otherwise
         token = st.get_state()
@@ -166,6 +180,69 @@ class OrderedStitcher:
         self._last = c
         self._local.pop(c - 2, None)
         return out
+
+
+class ShardedBitStream:
+    """Host samples in, the stitched bit stream out, on N GPUs: ``ShardedPipelines`` for the device work and an
+    ``OrderedStitcher`` for the bit post-processing of the chunks this rank owns.
+
+        bs = ShardedBitStream(pipelines, stitcher, rank, world, send, recv, first_chunk=pipelines.chunks_enqueued)
+        for block in blocks:                              # on EVERY rank, the same samples
+            buf = bs.next_buffer()                        # pinned chunk buffer of the pipeline the next chunk goes to
+            buf[:ovl] = previous tail; buf[ovl:] = block  # (after that pipeline's earlier H2D copy has completed)
+            bs.submit()
+        bs.finish()
+        bs.bits                                           # {chunk number: (bits, centres, trust)} of the owned chunks
+
+    ``send(token, dst, c)`` / ``recv(src, c)`` move the ≤ 1 KB carry of chunk ``c`` between ranks.  The last chunk's carry
+    is addressed to the owner of a chunk that never comes; ``finish`` takes it off the wire."""
+
+    def __init__(self, pipelines, stitcher, rank, world, send, recv, first_chunk=0):
+        self.sh, self.rank, self.world = pipelines, rank, world
+        self.K = len(pipelines.pipes)
+        self.first = self.next = first_chunk
+        self._recv = recv
+        self.ordered = OrderedStitcher(stitcher, rank, self.owner_of_chunk, send, recv, first_chunk)
+        self._owned = [deque() for _ in range(self.K)]
+        self.bits = {}
+
+    def owner_of_chunk(self, c):
+        return owner_of(c // self.K, self.world)          # ShardedPipelines: chunk c = local chunk c // K of pipeline c % K
+
+    @property
+    def next_pipe(self):
+        return self.next % self.K
+
+    def next_buffer(self):
+        return self.sh.pipes[self.next_pipe].engine.host_buffer
+
+    def _collector(self, pipe):
+        def collect(out):
+            c = self._owned[pipe].popleft()
+            res, _, sym, centre, mag = out
+            self.bits[c] = self.ordered(c, sym, centre, mag, (), float(res.sp_sym))
+            return c
+        return collect
+
+    def submit(self):
+        """The next chunk's samples are in ``next_buffer()``: enqueue it (H2D included).  Returns its chunk number."""
+        c, pipe = self.next, self.next_pipe
+        if self.owner_of_chunk(c) == self.rank:
+            self._owned[pipe].append(c)
+        self.sh.enqueue(c, None, collect=self._collector(pipe))
+        self.next += 1
+        return c
+
+    def drain(self):
+        """Finish every owned chunk in flight (in chunk order); the stream can go on afterwards."""
+        self.sh.drain([self._collector(j) for j in range(self.K)])
+
+    def finish(self):
+        self.drain()
+        last = self.next - 1
+        if last >= self.first and self.owner_of_chunk(last + 1) == self.rank and self.owner_of_chunk(last) != self.rank:
+            self._recv(self.owner_of_chunk(last), last)
+        return self.bits
 
 
 def gather_results(results, world, gather_object, rank):

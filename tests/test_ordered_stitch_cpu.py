@@ -114,6 +114,112 @@ def test_the_stream_needs_the_realignment():
     assert sum(len(s[0]) != len(f[0]) for s, f in zip(seq, fresh)) >= 2     # the carry changes some chunks by one bit
 
 
+class _Res:
+    xchg_timeout = 0
+    sp_sym = float(SPS)
+
+
+class _StubEngine:
+    """Stands in for ``_native.Engine`` in the host protocol: the "device" returns the symbol table of the chunk whose
+    tail was enqueued (pipeline j of K sees global chunk s * K + j as its local chunk s)."""
+    D = 64
+
+    def __init__(self, j, K, first, chunks):
+        self.j, self.K, self.first, self.chunks = j, K, first, chunks
+        self.host_buffer = np.zeros(8, np.complex64)
+        self.tail = None
+
+    def set_bin_range(self, lo, hi): pass
+    def peer_export(self): return b"\0" * 64
+    def peer_attach(self, *a): pass
+    def upload(self): pass
+    def upload_device(self, chunk): pass
+    def enqueue_search_push(self, seq, owner): pass
+
+    def enqueue_owner_tail(self, seq):
+        self.tail = seq * self.K + self.j
+
+    def fetch(self):
+        c = self.tail - self.first
+        if c < 0:
+            return (_Res(), None, None, None, None)
+        sym, centre, mag, _, _ = self.chunks[c]
+        return (_Res(), None, sym, centre, mag)
+
+
+def _stream_worker(rank, world, port, q, K, prior):
+    import faulthandler
+    faulthandler.dump_traceback_later(120, exit=True)       # a protocol deadlock must fail the test, not hang it
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        chunks = [(a, b, c, None, e) for a, b, c, _, e in _chunks()]
+        sh = sharded.ShardedPipelines([_StubEngine(j, K, prior, chunks) for j in range(K)], rank, world, all_gather)
+        for i in range(prior):                  # device-resident chunks before the host stream starts (as in bench.py)
+            sh.enqueue(i, 1, collect=lambda out: None)
+        sh.drain(lambda out: None)
+        assert sh.chunks_enqueued == prior
+        pending = []
+
+        def send(token, dst, c):
+            buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+            pending.append(dist.isend(buf, dst=dst, tag=c))
+
+        def recv(src, c):
+            buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            dist.recv(buf, src=src, tag=c)
+            return buf.numpy().tobytes()
+        bs = sharded.ShardedBitStream(sh, _stitcher(), rank, world, send, recv, first_chunk=prior)
+        for k in range(N_CHUNKS):
+            assert bs.next_buffer() is sh.pipes[(prior + k) % K].engine.host_buffer
+            assert bs.submit() == prior + k
+            if k == N_CHUNKS // 2:
+                bs.drain()                      # a drain in the middle of the stream must neither block nor lose the carry
+        mine = bs.finish()
+        for w in pending:
+            w.wait()
+        assert sorted(mine) == [c for c in range(prior, prior + N_CHUNKS) if bs.owner_of_chunk(c) == rank]
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object({c: [a.tolist() for a in v] for c, v in mine.items()}, parts, dst=0)
+        if rank == 0:
+            merged = {}
+            for p in parts:
+                merged.update(p)
+            q.put([merged[c] for c in range(prior, prior + N_CHUNKS)])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,K,prior", [(2, 2, 5), (4, 3, 7), (3, 1, 0), (4, 2, 16)])
+def test_host_stream_over_sharded_pipelines_is_exact_and_terminates(world, K, prior):
+    """``ShardedBitStream``: the whole N > 1 host protocol (what ``bench.py --gpus N`` runs for its e2e figure) with stub
+    engines.  Uneven pipelines (``prior`` not a multiple of K) and K = 3 are the cases in which draining pipeline by
+    pipeline deadlocked on the GPU box in round 1 (ranks waiting for each other's carries)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, q, K, prior)) for r in range(world)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    chunks = _chunks()
+    st = _stitcher()
+    want = [st(a, b, c, (), e) for a, b, c, _, e in chunks]
+    assert len(merged) == N_CHUNKS
+    for got, exp in zip(merged, want):
+        for g, e in zip(got, exp):
+            assert np.array_equal(np.asarray(g, dtype=np.uint8), e)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
