@@ -713,59 +713,72 @@ def main():
     # (sharded.OrderedStitcher) so that the bit stream is the one a single process produces.  Every rank ingests the whole
     # chunk ("one H2D per GPU"). ----
     if sh is not None:
-        from collections import deque
-        e2e_n = min(args.steps, 200) // (world * K) * (world * K) or world * K
-        blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
-        dems = [dem] + extra
-        bufs = [d.get_signalBufferHostPointer() for d in dems]
-        for b in bufs:
-            b[:] = 0
-        gloo = dist.new_group(backend="gloo")
-        sends = []
+        def e2e_sharded():
+            import datetime
+            e2e_n = min(args.steps, 200) // (world * K) * (world * K) or world * K
+            blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
+            dems = [dem] + extra
+            bufs = [d.get_signalBufferHostPointer() for d in dems]
+            for b in bufs:
+                b[:] = 0
+            gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=120))
+            sends = []
 
-        def send(token, dst, c):
-            buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
-            buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
-            sends.append(dist.isend(buf, dst=dst, tag=c, group=gloo))
+            def send(token, dst, c):
+                buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+                buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+                sends.append(dist.isend(buf, dst=dst, tag=c, group=gloo))
 
-        def recv(src, c):
-            buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
-            dist.recv(buf, src=src, tag=c, group=gloo)
-            return buf.numpy().tobytes()
-        bs = sharded.ShardedBitStream(sh, dem._stitch, rank, world, send, recv, first_chunk=sh.chunks_enqueued)
+            def recv(src, c):
+                buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+                dist.recv(buf, src=src, tag=c, group=gloo)
+                return buf.numpy().tobytes()
+            bs = sharded.ShardedBitStream(sh, dem._stitch, rank, world, send, recv, first_chunk=sh.chunks_enqueued)
 
-        def run(count):
-            for _ in range(count):
-                pipe, i = bs.next_pipe, bs.next
-                streams[pipe].synchronize()           # the pipeline's previous H2D has left the pinned buffer
-                raw = bufs[pipe]
-                raw[:ovl] = bufs[(i - 1) % K][-ovl:]   # overlap carry (demodulator_process.py:337)
-                raw[ovl:] = blocks[i % ring]
-                bs.submit()
-            bs.drain()                                # in chunk order: the carries travel from chunk to chunk
-        run((-bs.first) % (world * K) + world * K)    # warm-up: up to the next whole owner round, plus one round
-        torch.cuda.synchronize()
-        dist.barrier()
-        nb0 = sum(len(v[0]) for v in bs.bits.values())
-        t0 = time.perf_counter()
-        run(e2e_n)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        bs.finish()
-        nbits = [sum(len(v[0]) for v in bs.bits.values()) - nb0]
-        for w in sends:
-            w.wait()
-        nb = torch.tensor([nbits[0]], device="cuda", dtype=torch.int64)
+            def run(count):
+                for _ in range(count):
+                    pipe, i = bs.next_pipe, bs.next
+                    streams[pipe].synchronize()           # the pipeline's previous H2D has left the pinned buffer
+                    raw = bufs[pipe]
+                    raw[:ovl] = bufs[(i - 1) % K][-ovl:]   # overlap carry (demodulator_process.py:337)
+                    raw[ovl:] = blocks[i % ring]
+                    bs.submit()
+                bs.drain()                                # in chunk order: the carries travel from chunk to chunk
+            run((-bs.first) % (world * K) + world * K)    # warm-up: up to the next whole owner round, plus one round
+            torch.cuda.synchronize()
+            dist.barrier(group=gloo)                  # (gloo: it times out instead of hanging if a rank has dropped out)
+            nb0 = sum(len(v[0]) for v in bs.bits.values())
+            t0 = time.perf_counter()
+            run(e2e_n)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            bs.finish()
+            for w in sends:
+                w.wait()
+            return dt, sum(len(v[0]) for v in bs.bits.values()) - nb0, e2e_n
+
+        # a failure on any rank (or a carry that never arrives: the gloo group times out after 120 s) must not take the
+        # device-resident line with it: no NCCL collective runs inside the phase, every rank reports afterwards, and the
+        # figure is dropped everywhere if one of them failed
+        try:
+            dt, nbits, e2e_n = e2e_sharded()
+            failed = 0
+        except Exception as exc:                       # noqa: BLE001
+            print(f"bench: N > 1 end-to-end phase failed on rank {rank}: {exc!r}", file=sys.stderr)
+            dt, nbits, e2e_n, failed = 0.0, 0, 1, 1
+        agg = torch.tensor([float(failed), dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        nb = torch.tensor([nbits], device="cuda", dtype=torch.int64)
         dist.all_reduce(nb)
-        dt = float(dt.item())
-        e2e = {"value": step_samples * e2e_n / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * world,
-               "d2h_bytes_per_step": int(88 + 4 * D * M + 12 * eng.max_sym), "steps": e2e_n, "ms_per_step": dt / e2e_n * 1e3,
-               "bits_per_step": int(nb.item()) / e2e_n,
-               "api": "sharded.ShardedPipelines.enqueue(chunk=None) on every rank (samples in each rank's pinned buffer, H2D + "
-                      "bin-sharded search on all ranks, tail + D2H on the chunk's owner) + sharded.OrderedStitcher (bit "
-                      "post-processing on the owner, chunk-to-chunk carry passed owner to owner over gloo)",
-               "note": "max over ranks of the wall time between barriers"}
+        if agg[0].item() == 0:
+            dt = float(agg[1].item())
+            e2e = {"value": step_samples * e2e_n / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * world,
+                   "d2h_bytes_per_step": int(88 + 4 * D * M + 12 * eng.max_sym), "steps": e2e_n, "ms_per_step": dt / e2e_n * 1e3,
+                   "bits_per_step": int(nb.item()) / e2e_n,
+                   "api": "sharded.ShardedBitStream on every rank: samples in each pipeline's pinned buffer, H2D + bin-sharded search "
+                          "on all ranks (ShardedPipelines), tail + D2H on the chunk's owner, bit post-processing on the owner with "
+                          "the chunk-to-chunk carry passed owner to owner over gloo (OrderedStitcher)",
+                   "note": "max over ranks of the wall time between barriers"}
 
     if rank != 0:
         if dist is not None:
