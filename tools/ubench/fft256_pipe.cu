@@ -1,0 +1,95 @@
+// Micro-benchmark for the next round: where do the 28 % between the FMA-pipe floor (0.54 ms) and the measured time
+// (0.75 ms) of search_fs256_kernel go?  It runs the kernel's own building blocks (csrc/fft_core.cuh, csrc/kernels.cuh)
+// at the kernel's occupancy (128-thread CTAs, 4 per SM) in three shapes:
+//   MODE 0  butterflies only: filter product + two radix-16 passes + twiddles + |y|^2 epilogue, the exchange replaced by
+//           a register no-op (pure FMA-pipe stream: the ceiling if shared memory were free);
+//   MODE 1  + the real shared-memory exchange (16 STS.64 + 8 LDS.128 per transform);
+//   MODE 2  + the filter spectrum read from shared memory (8 LDS.128 per transform) = the kernel's mask loop.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I pycusdr_b200/csrc -o tools/ubench/fft256_pipe
+//        tools/ubench/fft256_pipe.cu ; run on the GPU box.  Prints ns per transform-lane and the fraction of the 489-slot floor.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+using namespace pcs;
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k(const float4* __restrict__ gs, float* out, int iters) {
+    __shared__ __align__(16) float2 sbuf[8][272];
+    __shared__ float4 s_g[8 * 128];
+    const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
+    for (int i = threadIdx.x; i < 8 * 128; i += 128) s_g[i] = gs[i];
+    __syncthreads();
+    float2 tw[16], xb[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        float s, c;
+        sincospif(-2.0f * (float)(t * r) / 256.0f, &s, &c);
+        tw[r] = make_float2(c, s);
+        xb[r] = make_float2(0.01f * (t + r), 0.02f * (t - r));
+    }
+    float2 acc = make_float2(0.f, 0.f);
+    float best = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int m = 0; m < 8; ++m) {
+            float2 v[16];
+            const float4* g4 = MODE == 2 ? s_g + m * 128 + t : nullptr;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const float4 q = MODE == 2 ? g4[rr * 16] : make_float4(tw[rr].x, tw[rr].y, tw[rr + 8].y, tw[rr + 8].x);
+                v[2 * rr] = cmul(xb[2 * rr], make_float2(q.x, q.y));
+                v[2 * rr + 1] = cmul(xb[2 * rr + 1], make_float2(q.z, q.w));
+            }
+            if (MODE >= 1) {
+                fft256_regs<+1>(v, sbuf[g], tw, t);
+            } else {
+                Dft<16, +1>::run(v);
+#pragma unroll
+                for (int r = 1; r < 16; ++r) v[r] = cmulc(v[dft_q<16>(r)], tw[r]);
+                Dft<16, +1>::run(v);
+            }
+#pragma unroll
+            for (int s = 0; s < 16; s += 2) {
+                const float m0 = cabs2(v[s]), m1 = cabs2(v[s + 1]);
+                acc = __fadd2_rn(acc, make_float2(m0, m1));
+                best = fmaxf(best, fmaxf(m0, m1));
+            }
+            xb[m] = make_float2(xb[m].x + 1e-9f * best, xb[m].y);      // keep the chain data dependent across masks
+        }
+    }
+    if (acc.x + acc.y + best == 123.456f) out[threadIdx.x] = acc.x;
+}
+
+template <int MODE>
+void run(const char* name, const float4* gs, float* out) {
+    const int iters = 200, grid = 148 * 4 * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k<MODE><<<grid, 128>>>(gs, out, iters);
+    cudaEventRecord(e0);
+    k<MODE><<<grid, 128>>>(gs, out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double transforms = (double)grid * 8 * iters * 8;           // CTAs x groups x iterations x masks
+    const double slots = transforms * 16 * 489;                       // lane-slots of the FMA pipe
+    const double avail = 148.0 * 128 * 1.965e9 * ms * 1e-3;
+    printf("%-34s %8.3f ms  %.3f us per 1000 transforms  FMA-pipe slots used / available = %.3f\n", name, ms,
+           ms * 1e3 / (transforms / 1e3), slots / avail);
+}
+
+int main() {
+    float4* gs;
+    float* out;
+    cudaMalloc(&gs, 8 * 128 * sizeof(float4));
+    cudaMemset(gs, 0x3c, 8 * 128 * sizeof(float4));
+    cudaMalloc(&out, 4096);
+    run<0>("butterflies only", gs, out);
+    run<1>("+ shared-memory exchange", gs, out);
+    run<2>("+ filter spectra from shared memory", gs, out);
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
