@@ -113,6 +113,10 @@ int pcs_upload(pcs_handle* h);
 int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int32_t cap, int32_t* n_clipped,
                            float* thresholds);
 
+/* clippedPeakI (dem_base:686-705): idx (ascending, unique: what pcs_upload_thresholded returns) with every gap shorter
+ * than min_gap (peakMinGap = 100) samples filled in.  Host only.  *n_out is the full count even when it exceeds cap. */
+int pcs_fill_gaps(const int64_t* idx, int32_t n, int32_t min_gap, int64_t* out, int32_t cap, int32_t* n_out);
+
 /* Same, but the chunk is already in HBM (device pointer to complex64[nfft]); no copy is made and the
  * buffer must stay valid until the next synchronising call. */
 int pcs_upload_device(pcs_handle* h, const void* d_chunk);

@@ -95,6 +95,7 @@ SYMBOLS = {
     "pcs_ingest_destroy": (C.c_int, [_P]),
     "pcs_snr_means": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pcs_mean_abs_c64": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
+    "pcs_fill_gaps": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pcs_chunk_to_bits": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.POINTER(C.c_int32), _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_sync_search": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
@@ -158,6 +159,17 @@ def mean_abs_c64(z):
     if rc != 0:
         raise NativeError(rc, load().pcs_last_error().decode())
     return np.float32(out.value)
+
+
+def fill_gaps(idx, min_gap, nfft):
+    """``clippedPeakI`` from ``clippedPeakIPure`` (dem_base:686-705, ``pcs_fill_gaps``; host only)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.empty(int(nfft), dtype=np.int64)
+    n = C.c_int32(0)
+    rc = load().pcs_fill_gaps(_ptr(idx), len(idx), int(min_gap), _ptr(out), len(out), C.byref(n))
+    if rc != 0:
+        raise NativeError(rc, load().pcs_last_error().decode())
+    return out[:min(n.value, len(out))].copy()
 
 
 def _ptr(a):

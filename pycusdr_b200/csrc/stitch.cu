@@ -223,6 +223,29 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
     return PCS_OK;
 }
 
+// clippedPeakI of __thresholdInput (dem_base:686-705): the clipped sample indices with every gap shorter than min_gap
+// samples between two of them filled in.  idx ascending and unique (what the clip pass returns); out ascending.
+int pcs_fill_gaps(const int64_t* idx, int32_t n, int32_t min_gap, int64_t* out, int32_t cap, int32_t* n_out) {
+    if (!n_out || n < 0 || (n > 0 && !idx) || cap < 0 || (cap > 0 && !out)) return pcs_fail_msg(PCS_ERR_INVALID, "bad argument");
+    int64_t k = 0;
+    auto emit = [&](int64_t v) {
+        if (k < cap) out[k] = v;
+        ++k;
+    };
+    for (int32_t i = 0; i < n; ++i) {
+        emit(idx[i]);
+        if (i + 1 < n) {
+            const int64_t step = idx[i + 1] - idx[i];
+            if (step < 1) return pcs_fail_msg(PCS_ERR_INVALID, "indices must be ascending and unique");
+            if (step > 1 && step < min_gap)
+                for (int64_t v = idx[i] + 1; v < idx[i + 1]; ++v) emit(v);
+        }
+    }
+    if (k > INT32_MAX) return pcs_fail_msg(PCS_ERR_INVALID, "too many indices");
+    *n_out = (int32_t)k;       // may exceed cap: the list was truncated
+    return PCS_OK;
+}
+
 // ---- decoder-side sync search ---------------------------------------------------------------
 // What decoder.py:96-104 does with NumPy on the bit stream the demodulator hands over:
 //   score = np.convolve(bits, mask)            (full convolution, mask = flipud(header * 2 - 1), protocol.get_mask())

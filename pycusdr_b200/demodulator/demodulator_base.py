@@ -188,7 +188,9 @@ class Demodulator:
         over, self.clipLevels = self._engine.upload_thresholded(np.float32(self.peakThresholdScale))
         self._pending = None
         self._bits_ready = None
-        self._set_clipped(over)
+        self.clippedPeakIPure = over
+        self.peakMinGap = 100
+        self.clippedPeakI = _native.fill_gaps(over, self.peakMinGap, self.Nfft) if len(over) else over.copy()
 
     def uploadAndFindUHF(self, samples):
         samples = self._as_chunk_buffer(samples)

@@ -82,3 +82,29 @@ def test_window_mean_of_magnitudes_matches_numpy():
         np.testing.assert_allclose(got, np.mean(np.abs(z)), rtol=1e-6)
     with pytest.raises(_native.NativeError):
         _native.mean_abs_c64(np.zeros(0, np.complex64))
+
+
+def test_gap_filling_of_clipped_indices_matches_the_numpy_statement():
+    """pcs_fill_gaps against the reference's own gap-filling statements (dem_base:686-705) on random index sets."""
+    rng = np.random.RandomState(11)
+    N = 4096
+    for trial in range(200):
+        n = int(rng.randint(0, 60))
+        over = np.unique(rng.randint(0, N, size=n)) if trial % 3 else np.unique(np.concatenate(
+            [rng.randint(0, N, size=max(n // 4, 1)) + k for k in (0, 1, 3, 50, 99, 100, 101)]) % N)
+        got = _native.fill_gaps(over, 100, N)
+        if len(over) == 0:
+            assert len(got) == 0
+            continue
+        # the reference's statements, verbatim in meaning
+        diffPeaks = np.diff(over)
+        gapsAll = np.where(diffPeaks > 1)[0]
+        gaps = np.where(diffPeaks[gapsAll] < 100)[0]
+        gapsLen, gapsIdx = diffPeaks[gapsAll[gaps]], gapsAll[gaps]
+        pp = np.zeros(N, dtype=np.int8)
+        pp[over] = 1
+        for i in range(len(gapsLen)):
+            pp[over[gapsIdx[i]]:over[gapsIdx[i]] + gapsLen[i]] = 1
+        np.testing.assert_array_equal(got, np.where(pp == 1)[0])
+    with pytest.raises(_native.NativeError):
+        _native.fill_gaps(np.array([5, 5], np.int64), 100, N)
