@@ -106,3 +106,37 @@ def test_sync_search_equals_numpy_convolve(seed):
     idx2, _ = _native.sync_search(bits, mask, -10)
     np.testing.assert_array_equal(idx2, np.where(score >= -10)[0])
     print(f"np.convolve {t_np * 1e3:.2f} ms, native {t_nat * 1e3:.2f} ms")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_injected_carry_is_the_references_state(seed):
+    """pcs_stitch_set_state / get_state speak the reference's own state variables (poswinP, posSymEnd, dem_base:977-979):
+    a stitcher primed with the oracle's state processes the next chunk exactly like the oracle, whatever it processed
+    before, and ends up holding the oracle's new state."""
+    rng = np.random.RandomState(100 + seed)
+    M, bitLUT = 8, np.array([0, 0, 1, 1, 0, 0, 1, 1])
+    mk = lambda: _native.Stitcher(nfft=N, overlap=OVL, overlap_offset=OO, error_threshold=ERR_THR,      # noqa: E731
+                                  match_threshold=MATCH_THR, bit_lut=bitLUT, symbol_lut=[])
+    chunks = _stream(rng, 8, M, 16, slip_at=(2, 5, 104), noisy_at=(3,))
+    state = O.OverlapState()
+    stray = mk()
+    for c, (sym, centres, mag) in enumerate(chunks):
+        if c == 2:
+            continue                                           # (the chunk with a -1 symbol is covered above)
+        fresh = mk()
+        if c % 2:
+            stray(*chunks[(c + 3) % 8 if (c + 3) % 8 != 2 else 4], [], 16.0)    # leave some unrelated carry behind
+            fresh = stray
+        pos = np.asarray(state.poswinP, dtype=np.uint8)
+        end = np.asarray(state.posSymEnd if state.posSymEnd is not None else [], dtype=np.uint8)
+        token = len(pos).to_bytes(2, "little") + len(end).to_bytes(2, "little") + pos.tobytes() + end.tobytes()
+        fresh.set_state(token)
+        assert fresh.get_state() == token
+        want = _oracle_chunk(state, sym, centres, mag, np.array([], dtype=np.int64), 16.0, bitLUT, [])
+        got = fresh(sym, centres, mag, [], 16.0)
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+        new = fresh.get_state()
+        a, b = int.from_bytes(new[:2], "little"), int.from_bytes(new[2:4], "little")
+        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, a, 4), np.asarray(state.poswinP, dtype=np.uint8))
+        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, b, 4 + a), np.asarray(state.posSymEnd, dtype=np.uint8))
