@@ -1,4 +1,6 @@
-"""torchrun script: bin-sharded search over NVLink peer memory vs the unsharded path on the same chunks, bit for bit."""
+"""torchrun script: (1) bin-sharded search over NVLink peer memory vs the unsharded path on the same chunks, bit for bit;
+(2) host samples in, stitched bits out through ShardedBitStream vs the class API of one process on the same stream
+(added after the round's GPU budget ended: part 2 has not run on GPUs yet)."""
 import os
 import sys
 
@@ -72,6 +74,60 @@ if rank == 0:
             print(f"chunk {i}: exchange timeout")
     print(f"sharded check: world {world}, {len(merged)} chunks, {bad} mismatches")
     ok = bad == 0
+
+# ---- host samples in, stitched bits out (ShardedBitStream) vs the class API of one process on the same stream ----
+from pycusdr_b200 import _native                                                  # noqa: E402
+gloo = dist.new_group(backend="gloo")
+pending = []
+
+
+def send(token, dst, c):
+    buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+    buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+    pending.append(dist.isend(buf, dst=dst, tag=c, group=gloo))
+
+
+def recv(src, c):
+    buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+    dist.recv(buf, src=src, tag=c, group=gloo)
+    return buf.numpy().tobytes()
+
+
+first = sh.chunks_enqueued
+bs = sharded.ShardedBitStream(sh, dem._stitch, rank, world, send, recv, first_chunk=first)
+n_host = len(sig) // step
+prev_tail = np.zeros(ovl, np.complex64)
+for c in range(n_host):
+    torch.cuda.synchronize()               # (a real host waits only for the pipeline's previous H2D copy)
+    raw = bs.next_buffer()
+    raw[:ovl] = prev_tail
+    raw[ovl:] = sig[c * step:(c + 1) * step]
+    prev_tail = raw[-ovl:].copy()
+    bs.submit()
+mine = bs.finish()
+for w in pending:
+    w.wait()
+parts = [None] * world if rank == 0 else None
+dist.gather_object({c: tuple(a.copy() for a in v) for c, v in mine.items()}, parts, dst=0)
+if rank == 0:
+    got_bits = {}
+    for p in parts:
+        got_bits.update(p)
+    one = UHF.Demodulator(conf, P, RADIO)
+    raw = one.get_signalBufferHostPointer()
+    raw[:] = 0
+    bad = 0
+    for c in range(n_host):
+        raw[ovl:] = sig[c * step:(c + 1) * step]
+        one.uploadAndFindCarrier(raw)
+        want = one.demodulate()[:3]
+        raw[:ovl] = raw[-ovl:]
+        for name, g, w in zip(("bits", "centres", "trust"), got_bits[first + c], want):
+            if not np.array_equal(g, w):
+                bad += 1
+                print(f"host stream chunk {c}: {name} differ ({len(g)} vs {len(w)})")
+    print(f"sharded host stream: world {world}, {n_host} chunks, {bad} mismatches against the single-process class API")
+    ok = ok and bad == 0
 dist.barrier()
 for d in dems:
     d._engine.close()
