@@ -221,20 +221,33 @@ class Stitcher:
     def reset(self):
         self.lib.pcs_stitch_reset(self._h)
 
-    STATE_BYTES = 1024
+    STATE_BYTES = 1024      # transport buffer that holds a token of every shipped geometry (state_capacity(...) <= 200)
+
+    @staticmethod
+    def state_capacity(overlap, overlap_offset, spsym_min, window_width=63):
+        """Upper bound in bytes of a ``get_state`` token for this geometry (for fixed-size transports): the carry holds
+        the symbols whose centre lies beyond ``nfft - overlap/2`` (poswinP, dem_base:977; symbols are at least
+        ``spsym_min`` samples apart and a centre is within ``window_width`` samples of its nominal position) and the last
+        ``overlap_offset + 1`` bits of the window (posSymEnd, dem_base:979), after an 8-byte header."""
+        return 8 + (int(overlap) // 2 + int(window_width)) // max(int(spsym_min), 1) + 2 + int(overlap_offset) + 1
 
     def get_state(self):
-        """The carry to the next chunk as ``bytes``: 2-byte counts (poswinP, posSymEnd) + the bits themselves."""
-        buf = np.empty(self.STATE_BYTES, dtype=np.uint8)
+        """The carry to the next chunk as ``bytes``: two 4-byte counts (poswinP, posSymEnd) + the bits themselves.
+        The lengths are queried first, so any geometry fits."""
         a, b = C.c_int32(0), C.c_int32(0)
-        rc = self.lib.pcs_stitch_get_state(self._h, _ptr(buf), self.STATE_BYTES - 4, C.byref(a), C.byref(b))
+        self.lib.pcs_stitch_get_state(self._h, None, 0, C.byref(a), C.byref(b))      # lengths only
+        n = a.value + b.value
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        rc = self.lib.pcs_stitch_get_state(self._h, _ptr(buf), n, C.byref(a), C.byref(b))
         if rc != 0:
             raise NativeError(rc, self.lib.pcs_last_error().decode())
-        return int(a.value).to_bytes(2, "little") + int(b.value).to_bytes(2, "little") + buf[:a.value + b.value].tobytes()
+        return int(a.value).to_bytes(4, "little") + int(b.value).to_bytes(4, "little") + buf[:n].tobytes()
 
     def set_state(self, token):
-        a, b = int.from_bytes(token[:2], "little"), int.from_bytes(token[2:4], "little")
-        buf = np.frombuffer(token, dtype=np.uint8, count=a + b, offset=4).copy() if a + b else np.empty(0, np.uint8)
+        a, b = int.from_bytes(token[:4], "little"), int.from_bytes(token[4:8], "little")
+        if len(token) < 8 + a + b:
+            raise ValueError(f"truncated stitcher state: {len(token)} bytes for counts {a} + {b}")
+        buf = np.frombuffer(token, dtype=np.uint8, count=a + b, offset=8).copy() if a + b else np.empty(0, np.uint8)
         rc = self.lib.pcs_stitch_set_state(self._h, _ptr(buf) if a + b else None, a, b)
         if rc != 0:
             raise NativeError(rc, self.lib.pcs_last_error().decode())

@@ -39,14 +39,16 @@ class Demodulator:
 
     def __init__(self, conf, protocol, radioName, fused=True, path=_native.PATH_AUTO, log2_block=0, use_graph=True,
                  native_post=True, groups_per_cta=0, xb_smem=False, search_form=0, items_per_cta=0, one_call=True,
-                 warps20=False, native_threshold=True):
+                 warps20=False, native_threshold=False):
         self.protocol = protocol
         self.radioName = radioName
         self.confRadio = confRadio = conf["Radios"]["Rx"][radioName]
         self.confGPU = confGPU = conf["GPU"][confRadio["CUDA_settings"]]
         self.fused = fused
         self.one_call = one_call
-        self.native_threshold = native_threshold      # STX backend: input clipping on the device
+        # STX backend: input clipping on the device (opt-in: agrees with the NumPy statement to 1e-6, not bit for bit,
+        # because np.abs(complex64) is a host-dependent SIMD approximation; see STX.py)
+        self.native_threshold = native_threshold
 
         # chunk geometry (dem_base:89-93)
         self.sigLen = 2 ** confGPU["blockSize"]
@@ -183,7 +185,10 @@ class Demodulator:
 
     def thresholdAndUpload(self, samples):
         """__thresholdInput + uploadToGPU with the clipping done on the device (``pcs_upload_thresholded``); the pinned
-        buffer ends up clipped in place exactly as the reference leaves it (dem_base:670-707, 548-558)."""
+        buffer ends up clipped in place like the reference leaves it (dem_base:670-707, 548-558) -- to 1e-6 relative in
+        the clipped samples and the two clip levels, exactly when the magnitudes are exact in any implementation.  The
+        level is float32(scale) * float32 mean, which is what ``peakThresholdScale * np.mean(mag)`` evaluates to under
+        NumPy >= 2 (a NumPy 1.x host rounds the float64 product once instead)."""
         self._as_chunk_buffer(samples)
         over, self.clipLevels = self._engine.upload_thresholded(np.float32(self.peakThresholdScale))
         self._pending = None

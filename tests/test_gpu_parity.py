@@ -366,7 +366,7 @@ def _stx_pair(blockSize=15, scale=4.5):
     conf = conf_variant("benchmark/bench_GMSK.json", blockSize=blockSize)
     conf["GPU"]["UHF"]["peakThresholdScale"] = scale
     P = protocol_for(conf)
-    return STX.Demodulator(conf, P, RADIO), STX.Demodulator(conf, P, RADIO, native_threshold=False)
+    return STX.Demodulator(conf, P, RADIO, native_threshold=True), STX.Demodulator(conf, P, RADIO, native_threshold=False)
 
 
 @pytest.mark.parametrize("blockSize", [12, 15, 18])

@@ -129,7 +129,7 @@ def test_injected_carry_is_the_references_state(seed):
             fresh = stray
         pos = np.asarray(state.poswinP, dtype=np.uint8)
         end = np.asarray(state.posSymEnd if state.posSymEnd is not None else [], dtype=np.uint8)
-        token = len(pos).to_bytes(2, "little") + len(end).to_bytes(2, "little") + pos.tobytes() + end.tobytes()
+        token = len(pos).to_bytes(4, "little") + len(end).to_bytes(4, "little") + pos.tobytes() + end.tobytes()
         fresh.set_state(token)
         assert fresh.get_state() == token
         want = _oracle_chunk(state, sym, centres, mag, np.array([], dtype=np.int64), 16.0, bitLUT, [])
@@ -137,6 +137,28 @@ def test_injected_carry_is_the_references_state(seed):
         for g, w in zip(got, want):
             np.testing.assert_array_equal(g, w)
         new = fresh.get_state()
-        a, b = int.from_bytes(new[:2], "little"), int.from_bytes(new[2:4], "little")
-        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, a, 4), np.asarray(state.poswinP, dtype=np.uint8))
-        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, b, 4 + a), np.asarray(state.posSymEnd, dtype=np.uint8))
+        a, b = int.from_bytes(new[:4], "little"), int.from_bytes(new[4:8], "little")
+        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, a, 8), np.asarray(state.poswinP, dtype=np.uint8))
+        np.testing.assert_array_equal(np.frombuffer(new, np.uint8, b, 8 + a), np.asarray(state.posSymEnd, dtype=np.uint8))
+
+
+def test_carry_of_a_large_overlap_fits_whatever_the_geometry():
+    """overlap 2^13 at 4 samples per symbol carries ~2 K bits; the token is sized from the stitcher's own lengths
+    (and state_capacity bounds it for fixed-size transports)."""
+    nfft, ovl, sps = 2 ** 15, 2 ** 13, 4
+    st = _native.Stitcher(nfft=nfft, overlap=ovl, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
+                          bit_lut=np.array([0, 0, 1, 1, 0, 0, 1, 1]), symbol_lut=[])
+    n = nfft // sps
+    rng = np.random.RandomState(3)
+    sym = rng.randint(0, 8, n).astype(np.int32)
+    centres = (np.arange(n) * sps + 1).astype(np.int32)
+    mag = rng.rand(n).astype(np.float32)
+    st(sym, centres, mag, [], float(sps))
+    token = st.get_state()
+    a, b = int.from_bytes(token[:4], "little"), int.from_bytes(token[4:8], "little")
+    assert a > 1020 and b == OO + 1 and len(token) == 8 + a + b
+    assert len(token) <= _native.Stitcher.state_capacity(ovl, OO, sps // 2, 7)
+    other = _native.Stitcher(nfft=nfft, overlap=ovl, overlap_offset=OO, error_threshold=ERR_THR, match_threshold=MATCH_THR,
+                             bit_lut=np.array([0, 0, 1, 1, 0, 0, 1, 1]), symbol_lut=[])
+    other.set_state(token)
+    assert other.get_state() == token
