@@ -188,19 +188,36 @@ int pcs_shard_buffers(pcs_handle* h, void** d_energy, void** d_peak_val, void** 
 int pcs_enqueue_search_local(pcs_handle* h);
 int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod);
 
-/* The same sharding without NCCL on the data path: the exchange goes through NVLink peer memory.  Every rank
- * exports one small exchange region (2 x three [D*M] tables + arrival flags) with CUDA IPC (pcs_peer_export, 64-byte
- * handle), the host all-gathers the handles once (any transport) and attaches them (pcs_peer_attach).  Per chunk
- * `seq`, every rank calls pcs_enqueue_search_push(seq, owner): its search / reduction kernels store their rows of the
- * tables directly into the OWNER's region (P2P stores) and a flag kernel publishes the arrival.  Only the owner calls
- * pcs_enqueue_owner_tail(seq): a wait kernel acquires all flags, then estimate + demod + result copies run on the
- * gathered table (identical to the single-GPU table), and pcs_fetch collects them.  Owners rotate (seq % world), so
- * the non-sharded tail costs each rank 1/world of a chunk.  Regions are double-buffered by (seq / world) parity; a
- * rank must enqueue chunks in increasing seq order. */
-int pcs_peer_export(pcs_handle* h, void* ipc_handle_out /* 64 bytes */);
-int pcs_peer_attach(pcs_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
-int pcs_enqueue_search_push(pcs_handle* h, int64_t seq, int32_t owner);
-int pcs_enqueue_owner_tail(pcs_handle* h, int64_t seq);
+/* Bin-sharded STREAMING search without a collective on the data path (replaces, for N GPUs, the chunk loop
+ * of pyCuSDR/demodulator_process.py:284-338 around uploadAndFindCarrier / demodulate, and sigFIFO.py:147-181 as the one
+ * source of samples).  One process and one handle per GPU, every handle created with the FULL shift table.
+ *   - rank 0 is the ingest rank: it alone receives samples (PCS_SRC_HOST: a host pointer, or NULL after writing into the
+ *     pinned slot pcs_shard_host_slot returned; PCS_SRC_DEVICE: a device pointer).  The chunk is copied once into rank 0's
+ *     HBM and from there into every peer's chunk ring over NVLink by the copy engines; a data flag tells the peer's stream.
+ *   - every rank searches its slice of the Doppler bins; the finishing CTAs of its search kernel store the slice's rows of
+ *     the three [D][M] tables straight into the exchange region of the chunk's OWNER (seq % world) and raise a row flag.
+ *   - the owner alone runs estimate + demodulation + timing + symbol decisions on the gathered tables (the very tables one
+ *     GPU produces: results are bit-identical to pcs_process) and keeps the results in one of four result stages until
+ *     pcs_shard_fetch collects them.
+ * pcs_shard_init allocates the exchange region (tables, flags, chunk ring of `ring` slots: even, <= 2 * world, 0 = choose)
+ * and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles with any transport and passes them, in rank
+ * order, to pcs_shard_attach.  pcs_shard_submit(seq) is then called on EVERY rank for seq = 0, 1, 2, ... (src is ignored
+ * on ranks other than 0); it never blocks on another rank.  The owner must fetch chunk seq before it submits chunk
+ * seq + 4 * world.  A handle initialised for sharding is dedicated to it.  world = 1 is allowed (a single GPU streaming
+ * through the same engine). */
+enum { PCS_SRC_DEVICE = 1, PCS_SRC_HOST = 2 };
+int pcs_shard_init(pcs_handle* h, int32_t rank, int32_t world, int32_t ring, void* ipc_handle_out /* 64 bytes */);
+int pcs_shard_attach(pcs_handle* h, const void* ipc_handles /* world x 64 bytes, rank order */);
+int pcs_shard_info(const pcs_handle* h, int32_t* ring, int32_t* lanes, int32_t* bin_lo, int32_t* bin_hi, int32_t* stages);
+int pcs_shard_host_slot(pcs_handle* h, int64_t seq, void** out /* pinned complex64[nfft] for chunk seq (rank 0) */);
+int pcs_shard_submit(pcs_handle* h, int64_t seq, int32_t src_kind, const void* src);
+/* Owner only; blocks until the tail of chunk seq has finished.  res->xchg_timeout != 0: a peer's rows or the chunk never
+ * arrived (bit 0) or a flag overran (bit 1) -- the results are then not valid.  sig_mean / noise_mean / snr_ok as in
+ * pcs_snr_means.  Any output pointer may be NULL. */
+int pcs_shard_fetch(pcs_handle* h, int64_t seq, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag,
+                    float* sig_mean, float* noise_mean, int32_t* snr_ok);
+int pcs_shard_sync(pcs_handle* h);
+int pcs_shard_streams(const pcs_handle* h, uint64_t* out4 /* lane 0, lane 1, copy, tail (cudaStream_t as integers) */);
 
 /* Make the handle enqueue on a caller-owned stream (cudaStream_t as an integer), e.g. the framework
  * stream NCCL collectives are ordered on.  The handle's own stream is destroyed. */

@@ -78,10 +78,16 @@ SYMBOLS = {
     "pcs_shard_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "pcs_enqueue_search_local": (C.c_int, [_P]),
     "pcs_enqueue_estimate_and_demod": (C.c_int, [_P, C.c_int32]),
-    "pcs_peer_export": (C.c_int, [_P, _P]),
-    "pcs_peer_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
-    "pcs_enqueue_search_push": (C.c_int, [_P, C.c_int64, C.c_int32]),
-    "pcs_enqueue_owner_tail": (C.c_int, [_P, C.c_int64]),
+    "pcs_shard_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "pcs_shard_attach": (C.c_int, [_P, _P]),
+    "pcs_shard_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]),
+    "pcs_shard_host_slot": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
+    "pcs_shard_submit": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
+    "pcs_shard_fetch": (C.c_int, [_P, C.c_int64, C.POINTER(Result), _P, _P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                  C.POINTER(C.c_int32)]),
+    "pcs_shard_sync": (C.c_int, [_P]),
+    "pcs_shard_streams": (C.c_int, [_P, _P]),
     "pcs_stitch_create": (C.c_int, [C.POINTER(StitchConfig), _P, _P, C.POINTER(_P)]),
     "pcs_stitch_chunk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_stitch_reset": (C.c_int, [_P]),
@@ -391,6 +397,7 @@ class Engine:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             self.host_buffer = None
+            self._slots = {}
             self._h = None
             self.lib.pcs_destroy(h)
 
@@ -528,24 +535,61 @@ class Engine:
     def enqueue_estimate_and_demod(self, with_demod=True):
         self._check(self.lib.pcs_enqueue_estimate_and_demod(self._h, int(bool(with_demod))))
 
-    # -- bin sharding over NVLink peer memory ------------------------------------------------------
-    def peer_export(self):
-        """64-byte CUDA IPC handle of this handle's exchange region."""
+    # -- bin-sharded streaming search over NVLink peer memory (pcs_shard_*) ---------------------------
+    def shard_init(self, rank, world, ring=0):
+        """Allocate the exchange region / chunk ring; returns its 64-byte CUDA IPC handle."""
         buf = C.create_string_buffer(64)
-        self._check(self.lib.pcs_peer_export(self._h, buf))
+        self._check(self.lib.pcs_shard_init(self._h, int(rank), int(world), int(ring), buf))
+        self._shard_world = int(world)
+        self._slots = {}
         return buf.raw
 
-    def peer_attach(self, rank, world, handles):
+    def shard_attach(self, handles):
         blob = b"".join(handles)
-        if len(blob) != 64 * world:
+        if len(blob) != 64 * self._shard_world:
             raise ValueError("need one 64-byte IPC handle per rank")
-        self._check(self.lib.pcs_peer_attach(self._h, int(rank), int(world), C.c_char_p(blob)))
+        self._check(self.lib.pcs_shard_attach(self._h, C.c_char_p(blob)))
 
-    def enqueue_search_push(self, seq, owner):
-        self._check(self.lib.pcs_enqueue_search_push(self._h, int(seq), int(owner)))
+    def shard_info(self):
+        v = [C.c_int32(0) for _ in range(5)]
+        self._check(self.lib.pcs_shard_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("ring", "lanes", "bin_lo", "bin_hi", "stages"), (x.value for x in v)))
 
-    def enqueue_owner_tail(self, seq):
-        self._check(self.lib.pcs_enqueue_owner_tail(self._h, int(seq)))
+    def shard_host_slot(self, seq):
+        """Ingest rank: NumPy view (complex64[nfft]) of the pinned slot chunk ``seq`` is read from."""
+        p = _P()
+        self._check(self.lib.pcs_shard_host_slot(self._h, int(seq), C.byref(p)))
+        view = self._slots.get(p.value)
+        if view is None:
+            buf = (C.c_float * (2 * self.nfft)).from_address(p.value)
+            view = self._slots[p.value] = np.frombuffer(buf, dtype=np.complex64)
+        return view
+
+    def shard_submit(self, seq, kind, src=None):
+        """``src``: device pointer (int), host ndarray (complex64[nfft], contiguous) or None."""
+        if isinstance(src, np.ndarray):
+            if src.dtype != np.complex64 or not src.flags.c_contiguous or src.size != self.nfft:
+                raise ValueError("host chunk must be a contiguous complex64[nfft] array")
+            src = _ptr(src)
+        self._check(self.lib.pcs_shard_submit(self._h, int(seq), int(kind), _P(src) if src else None))
+
+    def shard_fetch(self, seq):
+        """Owner: ``(res, E, sym, centre, mag, snr_means or None)`` of chunk ``seq`` (views into the engine's buffers)."""
+        res, a, b, ok = Result(), C.c_float(0), C.c_float(0), C.c_int32(0)
+        self._check(self.lib.pcs_shard_fetch(self._h, int(seq), C.byref(res), _ptr(self._E), _ptr(self._sym), _ptr(self._centre),
+                                             _ptr(self._mag), C.byref(a), C.byref(b), C.byref(ok)))
+        n = res.n_sym
+        means = (np.float32(a.value), np.float32(b.value)) if ok.value else None
+        return res, self._E, self._sym[:n], self._centre[:n], self._mag[:n], means
+
+    def shard_sync(self):
+        self._check(self.lib.pcs_shard_sync(self._h))
+
+    def shard_streams(self):
+        """(lane 0, lane 1, copy, tail) CUDA streams of the engine as integers."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.pcs_shard_streams(self._h, out))
+        return tuple(int(v) for v in out)
 
     def set_stream(self, stream_ptr):
         self._check(self.lib.pcs_set_stream(self._h, int(stream_ptr)))

@@ -420,21 +420,30 @@ struct Fs256Params {
     const float4* __restrict__ xbs;     // [nblk][8][16] float4: block spectra, lane-major pairs (X[t+32rr], X[t+32rr+16])
     const float4* __restrict__ gs;      // [D][M][8][16] float4: Doppler-shifted filter spectra (x N/256), same layout
     const float2* __restrict__ tw;      // [256] exp(-2 pi i t / 256)
-    float* __restrict__ psum;           // [nblk][D][M]
-    float* __restrict__ pmax;           // [nblk][D][M]
+    float* __restrict__ psum;           // [D][nblk][M]  per-item partials, bin-major: a bin's partials are contiguous
+    float* __restrict__ pmax;           // [D][nblk][M]
     int N, D, M, nblk, V, Lpos, items_per_cta;
+    // fused finish (see fs256_finish_bin): the CTA that completes a bin reduces and locates it
+    unsigned int* __restrict__ bin_count;   // [D] items of the bin finished so far in this launch (self-resetting)
+    unsigned int* __restrict__ bins_done;   // bins finished in this launch (self-resetting)
+    float* __restrict__ Efull;          // [D][M] rows of this launch's bin range (kern:442 scale); may be peer memory
+    float* __restrict__ peak_val;       // [D][M]
+    int* __restrict__ peak_off;         // [D][M]
+    unsigned long long* arrival_flag;   // when non-null: raised (system-scope release) once every bin's rows are stored
+    unsigned long long arrival_value;
 };
 
 // Block spectra of the chunk: block b = FFT_256(x[(b V - Lpos + i) % N], i = 0..255), one 16-lane group per block.
-__global__ void __launch_bounds__(256) block_spectra256_kernel(const float2* __restrict__ x, const float2* __restrict__ twg,
-                                                               float4* __restrict__ xbs, int N, int nblk, int V, int Lpos) {
-    __shared__ __align__(16) float2 sbuf[16][272];
+template <int G>      // groups (blocks) per CTA
+__global__ void __launch_bounds__(G * 16) block_spectra256_kernel(const float2* __restrict__ x, const float2* __restrict__ twg,
+                                                                  float4* __restrict__ xbs, int N, int nblk, int V, int Lpos) {
+    __shared__ __align__(16) float2 sbuf[G][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2 tw[16];
 #pragma unroll
     for (int r = 1; r < 16; ++r) tw[r] = __ldg(&twg[(t * r) & 255]);
     tw[0] = make_float2(1.f, 0.f);
-    int blk = blockIdx.x * 16 + g;
+    int blk = blockIdx.x * G + g;
     const bool live = blk < nblk;
     if (!live) blk = nblk - 1;
     const uint32_t nmask = (uint32_t)N - 1u, n_first = (uint32_t)(blk * V - Lpos) & nmask;
@@ -486,9 +495,130 @@ PCS_DEVINL unsigned fs256_valid_mask(int Lpos, int vlen, int t) {
     return vm;
 }
 
+// Fused finish of one Doppler bin, run by the CTA whose items completed the bin (every thread of the CTA calls it):
+//   1. E[d][m] = 2^-18 * sum over the bin's nblk block partials and the (value, block) of the largest |y|^2, in a fixed
+//      order that depends on nblk only -- 16 interleaved lanes per column (lane j takes blocks j, j + 16, ... in
+//      increasing order), then the 16 lane results in lane order -- so E is bit-identical for every CTA tiling, group count
+//      and bin sharding (kern:421-480 uses float atomics: not reproducible even run to run);
+//   2. the offset of the maximum inside the winning block of every mask (lowest sample index wins ties): the block is
+//      recomputed with the bin's filter spectra, which are still in shared memory;
+//   3. the bin's row of the three tables is stored (into the owner's exchange region over NVLink when the search is bin-
+//      sharded), and the CTA that finishes the launch's last bin raises the arrival flag with a system-scope release.
+// No separate reduction / locate / flag kernels remain on the per-chunk path of the shifted-filter search.
+#define PCS_FIN_LANES 16
+template <int G>
+PCS_DEVINL void fs256_finish_bin(const Fs256Params& p, int d, const float4* s_g, float2* buf, const float2* tw,
+                                 float (*s_red)[PCS_FIN_LANES][16], int* s_wblk) {
+    constexpr int NT = G * 16;
+    const int tid = threadIdx.x, t = tid & 15, g = tid >> 4;
+    const int MP = p.M <= 1 ? 1 : p.M <= 2 ? 2 : p.M <= 4 ? 4 : p.M <= 8 ? 8 : 16;     // columns padded to a power of two
+    const int tpc = min(NT / MP, PCS_FIN_LANES), lpt = PCS_FIN_LANES / tpc;              // threads per column, lanes per thread
+    const int m = tid % MP, jt = tid / MP;
+    if (m < p.M && jt < tpc) {
+        const float* __restrict__ ps = p.psum + (size_t)d * p.nblk * p.M + m;
+        const float* __restrict__ pm = p.pmax + (size_t)d * p.nblk * p.M + m;
+        for (int l = 0; l < lpt; ++l) {
+            const int lane = jt * lpt + l;
+            float sum = 0.f, best = -1.f;
+            int bb = 0x7fffffff;
+            int b = lane;
+            constexpr int U = 8, STEP = PCS_FIN_LANES;
+            for (; b + (U - 1) * STEP < p.nblk; b += U * STEP) {       // U independent L2 loads in flight, same summation order
+                float s8[U], v8[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    s8[u] = __ldcg(ps + (size_t)(b + u * STEP) * p.M);    // written by other SMs in this launch: bypass L1
+                    v8[u] = __ldcg(pm + (size_t)(b + u * STEP) * p.M);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    sum += s8[u];
+                    if (v8[u] > best) { best = v8[u]; bb = b + u * STEP; }
+                }
+            }
+            for (; b < p.nblk; b += STEP) {
+                sum += __ldcg(ps + (size_t)b * p.M);
+                const float v = __ldcg(pm + (size_t)b * p.M);
+                if (v > best) { best = v; bb = b; }
+            }
+            s_red[0][lane][m] = sum;
+            s_red[1][lane][m] = best;
+            s_red[2][lane][m] = __int_as_float(bb);
+        }
+    }
+    __syncthreads();
+    if (tid < p.M) {
+        float sum = s_red[0][0][tid], best = s_red[1][0][tid];
+        int bb = __float_as_int(s_red[2][0][tid]);
+#pragma unroll
+        for (int l = 1; l < PCS_FIN_LANES; ++l) {
+            sum += s_red[0][l][tid];
+            const float v = s_red[1][l][tid];
+            const int bl = __float_as_int(s_red[2][l][tid]);
+            if (v > best || (v == best && bl < bb)) { best = v; bb = bl; }
+        }
+        if (bb == 0x7fffffff) bb = 0;
+        p.Efull[(size_t)d * p.M + tid] = sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
+        p.peak_val[(size_t)d * p.M + tid] = best;
+        s_wblk[tid] = bb;
+    }
+    __syncthreads();
+    for (int m0 = 0; m0 < p.M; m0 += G) {          // group g recomputes the winning block of mask m0 + g
+        int mm = m0 + g;
+        const bool live = mm < p.M;
+        if (!live) mm = p.M - 1;                   // keep both halves of every warp convergent (full-mask shuffles below)
+        const int wblk = s_wblk[mm];
+        float2 xb[16], v[16];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const float4 q = __ldg(&p.xbs[(size_t)wblk * 128 + rr * 16 + t]);
+            xb[2 * rr] = make_float2(q.x, q.y);
+            xb[2 * rr + 1] = make_float2(q.z, q.w);
+        }
+        fs256_filter(s_g + (size_t)mm * 128 + t, xb, buf, tw, t, v);
+        const int n0 = wblk * p.V, vlen = min(p.V, p.N - n0);
+        float best = -1.f;
+        int idx = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int rel = t + 16 * dft_q<16>(s) - p.Lpos;
+            if (rel >= 0 && rel < vlen) {
+                const float mag = cabs2(v[s]);
+                const int n = n0 + rel;
+                if (mag > best || (mag == best && n < idx)) { best = mag; idx = n; }
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+        if (live && t == 0) p.peak_off[(size_t)d * p.M + mm] = idx == 0x7fffffff ? 0 : idx;
+    }
+    // publish: every thread's table stores are fenced (system scope when they went to a peer), then one thread counts the
+    // bin; the CTA that counts the last one raises the flag
+    if (p.arrival_flag != nullptr) __threadfence_system(); else __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        p.bin_count[d] = 0;                        // ready for the next launch on these buffers
+        const unsigned int prev = atomicAdd(p.bins_done, 1u);
+        if (prev == (unsigned int)p.D - 1u) {
+            *p.bins_done = 0;
+            if (p.arrival_flag != nullptr) {
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.arrival_flag), "l"(p.arrival_value) : "memory");
+            }
+        }
+    }
+}
+
 template <int G, int WARPS_PER_SM = 16>     // G = groups (half warps) per CTA; WARPS_PER_SM sets the register budget
 __global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_kernel(Fs256Params p) {
     __shared__ __align__(16) float2 sbuf[G][272];
+    __shared__ float s_red[3][PCS_FIN_LANES][16];
+    __shared__ int s_wblk[16];
+    __shared__ int s_last;
     extern __shared__ float4 s_dyn[];         // [M][128] float4 filter spectra of the current bin | [G][2][M][17] float partials
     float4* s_g = s_dyn;
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
@@ -558,7 +688,7 @@ __global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_ker
                     best = fmaxf(best, acc_max[m * 17 + l]);
                 }
                 if (live) {
-                    const size_t o = ((size_t)blk * p.D + d) * p.M + m;
+                    const size_t o = ((size_t)d * p.nblk + blk) * p.M + m;
                     p.psum[o] = sum;
                     p.pmax[o] = best;
                 }
@@ -566,6 +696,18 @@ __global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_ker
             __syncwarp();                     // the fold has read the partials before the next item overwrites them
         }
         cur += nb;
+        // count this CTA's items of the bin; whoever completes the bin reduces and locates it
+        __syncthreads();                      // every group's partials are stored
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int prev = atomicAdd(&p.bin_count[d], (unsigned int)nb);
+            s_last = (prev + (unsigned int)nb == (unsigned int)p.nblk);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            fs256_finish_bin<G>(p, d, s_g, buf, tw, s_red, s_wblk);
+        }
     }
 }
 
@@ -631,8 +773,7 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
                                                                 float* __restrict__ Efull, float* __restrict__ peak_val,
                                                                 int* __restrict__ peak_off, unsigned int* done_counter,
                                                                 unsigned long long* arrival_flag,
-                                                                unsigned long long arrival_value,
-                                                                const float4* __restrict__ xbs, const float4* __restrict__ gs) {
+                                                                unsigned long long arrival_value) {
     __shared__ __align__(16) float2 sbuf[16][272];
     const int t = threadIdx.x & 15, g = threadIdx.x >> 4;
     float2* buf = sbuf[g];
@@ -664,18 +805,8 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
     }
     const Os256Item it = os256_item(p, (long long)wblk * p.D + d);
     float2 xb[16], v[16];
-    if (xbs != nullptr) {      // shifted-filter form: the very products the search kernel evaluated
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const float4 q = __ldg(&xbs[(size_t)wblk * 128 + rr * 16 + t]);
-            xb[2 * rr] = make_float2(q.x, q.y);
-            xb[2 * rr + 1] = make_float2(q.z, q.w);
-        }
-        fs256_filter(gs + (size_t)col * 128 + t, xb, buf, tw, t, v);
-    } else {
-        os256_block_spectrum(p, it, buf, tw, t, xb);
-        os256_filter(p, m, xb, buf, tw, t, v);
-    }
+    os256_block_spectrum(p, it, buf, tw, t, xb);
+    os256_filter(p, m, xb, buf, tw, t, v);
     float best = -1.f;
     int idx = 0x7fffffff;
 #pragma unroll
@@ -1439,31 +1570,61 @@ __global__ void __launch_bounds__(128) threshold_clip_kernel(float2* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Peer exchange (bin sharding over NVLink): arrival flags in the owner's exchange region.
+// Peer exchange (bin sharding over NVLink): monotonic 64-bit sequence flags in the ranks' exchange regions, written with
+// system-scope releases by kernels of one GPU and acquired by tiny wait kernels of another.  A wait gives up after ~3 s
+// (a peer died) and records it instead of hanging the GPU; a flag NEWER than the one waited for where that cannot
+// legally happen (row flags: the back-pressure of pcs_shard_submit forbids it) is recorded as an overrun.
 // ---------------------------------------------------------------------------------------------
+#define PCS_WAIT_CYCLES 6000000000ll
+PCS_DEVINL unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+PCS_DEVINL void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// flags[i] = value for up to 32 destinations (possibly on other GPUs), after everything earlier in the stream.
+struct FlagList {
+    unsigned long long* dst[16];
+    int n;
+};
+__global__ void flags_set_kernel(FlagList f, unsigned long long value) {
+    __threadfence_system();
+    if ((int)threadIdx.x < f.n) st_release_sys(f.dst[threadIdx.x], value);
+}
 __global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {
     // the rows were stored by the preceding kernels of this stream; make them visible system-wide, then publish
     __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+    st_release_sys(flag, value);
 }
 
-// One lane per peer spins (with back-off) until that peer's flag reaches `want`; gives up after ~2 s and marks the
-// result block (status 2) instead of hanging the GPU if a peer died.
-__global__ void peer_wait_kernel(const unsigned long long* flags, int world, unsigned long long want, DevResult* res) {
-    const int r = threadIdx.x;
-    bool ok = true;
-    if (r < world) {
+// Lane i < n spins until flags[i * stride] >= want[i] (want 0 = nothing to wait for).  err (device word, may be null)
+// gets bit 0 on a timeout.  exact != 0: a flag beyond `want` sets bit 1 (overrun).  res (may be null): xchg_timeout.
+struct WaitList {
+    const unsigned long long* src[20];
+    unsigned long long want[20];
+    int n;
+};
+__global__ void flags_wait_kernel(WaitList w, int exact, int* err, DevResult* res) {
+    const int i = threadIdx.x;
+    int bad = 0;
+    if (i < w.n && w.want[i] != 0ull) {
         const long long t0 = clock64();
         for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
-            if (v >= want) break;
-            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
-            __nanosleep(200);
+            const unsigned long long v = ld_acquire_sys(w.src[i]);
+            if (v >= w.want[i]) {
+                if (exact && v > w.want[i]) bad = 2;
+                break;
+            }
+            if (clock64() - t0 > PCS_WAIT_CYCLES) { bad = 1; break; }
+            __nanosleep(100);
         }
     }
-    const unsigned all_ok = __all_sync(0xffffffffu, ok);
-    if (r == 0) res->xchg_timeout = all_ok ? 0 : 1;
+    const unsigned any = __ballot_sync(0xffffffffu, bad != 0);
+    if (bad && err) atomicOr(err, bad);
+    if (i == 0 && res) res->xchg_timeout = any ? 1 : 0;
     __threadfence_system();
 }
 

@@ -70,6 +70,7 @@ struct pcs_handle {
     float2 *d_Pf = nullptr, *d_ycplx = nullptr, *d_sigwin = nullptr, *d_noisewin = nullptr;
     const float2* d_x_cur = nullptr;   // chunk source of the current upload (d_x or external)
     int* d_shifts = nullptr;
+    std::vector<int32_t> h_shifts;     // host copy of the shift table (computeSNR window geometry)
     float *d_psum = nullptr, *d_pmax = nullptr, *d_Efull = nullptr, *d_E = nullptr, *d_peakv = nullptr;
     int *d_pidx = nullptr, *d_peako = nullptr;
     float *d_ymag = nullptr, *d_p = nullptr, *d_mag = nullptr;
@@ -89,10 +90,18 @@ struct pcs_handle {
     float *d_thr_partial = nullptr, *d_thr_level = nullptr;   // pcs_upload_thresholded (allocated on first use)
     unsigned int *d_thr_bits = nullptr, *h_thr_bits = nullptr;
     bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
-    float4 *d_xbs = nullptr, *d_gs = nullptr;
+    float4* d_gs = nullptr;
+    // per-launch working set of the shifted-filter search; a second set lets two chunks' searches overlap on two streams
+    // (bin sharding: pcs_shard_*), cur_lane selects the one the next enqueue uses
+    struct Fs256Bufs {
+        float4* xbs = nullptr;                       // block spectra of the chunk
+        float *psum = nullptr, *pmax = nullptr;      // [D][nblk][M] per-item partials
+        unsigned int *bin_count = nullptr, *bins_done = nullptr;
+    } fsb[2];
+    int cur_lane = 0;
     float2 *d_xbs_os = nullptr, *d_gs_os = nullptr;    // the same for the generic kernel (natural order)
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
-    float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;
+    float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;   // rotate-form kernels
     int* d_part_blk = nullptr;
     float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
     // Parseval variant (labelled alternative: energies only, no peak)
@@ -105,17 +114,12 @@ struct pcs_handle {
     bool graph_enabled = true, graph_failed = false, fetch_in_flight = false;
     int eager_chunks = 0;
     int64_t graph_launches = 0;
-    // bin-sharded search over NVLink peer memory (one process per GPU): exchange region = 2 x {E, peak value,
-    // peak offset}[D*M] + 2 x PCS_MAX_PEERS arrival flags, exported with CUDA IPC and written by the peers' kernels
-    unsigned char* d_xchg = nullptr;
-    size_t xchg_bytes = 0;
-    unsigned char* peer_base[16] = {};
-    int peer_rank = 0, peer_world = 0;
-    bool peers_attached = false, tail_on_side = false;
-    unsigned int* d_done = nullptr;                       // CTA completion counter of the locate kernel
+    // bin-sharded streaming search over NVLink peer memory (one process per GPU, pcs_shard_*): see the section at the
+    // end of this file for the layout of the exchange region and the flag protocol
+    struct Shard* shard = nullptr;
+    unsigned int* d_done = nullptr;                       // CTA completion counter of the locate kernel (rotate-form search)
     unsigned long long* push_flag = nullptr;              // when set, the search stage publishes its arrival there
     unsigned long long push_value = 0;
-    cudaEvent_t ev_push = nullptr;
     float *tab_E = nullptr, *tab_pv = nullptr;   // tables the search stage writes / the estimate stage reads
     int* tab_po = nullptr;
     cudaStream_t side = nullptr;       // forked branch of the graph: chunk spectrum -> SNR bins (off the critical path)
@@ -424,6 +428,21 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
     return 0;
 }
 
+// Working set of one in-flight shifted-filter search (see pcs_handle::fsb).
+static int alloc_fs256_lane(pcs_handle* h, int lane) {
+    pcs_handle::Fs256Bufs& b = h->fsb[lane];
+    if (b.xbs) return 0;
+    const size_t np = (size_t)h->nblk256 * h->D * h->M;
+    if (int rc = dev_alloc(h, &b.xbs, (size_t)h->nblk256 * 128)) return rc;
+    if (int rc = dev_alloc(h, &b.psum, np)) return rc;
+    if (int rc = dev_alloc(h, &b.pmax, np)) return rc;
+    if (int rc = dev_alloc(h, &b.bin_count, (size_t)h->D + 1)) return rc;
+    b.bins_done = b.bin_count + h->D;
+    CUDA_TRY(cudaMemsetAsync(b.bin_count, 0, sizeof(unsigned int) * ((size_t)h->D + 1), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // Search plan for filters short enough for 256-point blocks (at least half of every block is valid output).
 static int plan_fast256(pcs_handle* h, const float* masks_host) {
     const int N = h->N, M = h->M, D = h->D;
@@ -447,20 +466,13 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
     CUDA_TRY(cudaMemcpyAsync(h->d_gperm, gp.data(), sizeof(float4) * gp.size(), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     const size_t np = (size_t)h->nblk256 * D * M;
-    if (int rc = dev_alloc(h, &h->d_psum256, np)) return rc;
-    if (int rc = dev_alloc(h, &h->d_pmax256, np)) return rc;
-    if (int rc = dev_alloc(h, &h->d_part_sum, (size_t)PCS_RED_SLICES * D * M)) return rc;
-    if (int rc = dev_alloc(h, &h->d_part_max, (size_t)PCS_RED_SLICES * D * M)) return rc;
-    if (int rc = dev_alloc(h, &h->d_part_blk, (size_t)PCS_RED_SLICES * D * M)) return rc;
-    if (int rc = dev_alloc(h, &h->d_done, (size_t)1)) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
     h->fast256 = true;
     // Shifted-filter form (default): per-bin filter spectra gathered once from the protocol's spectra, block spectra of
     // the unrotated chunk once per chunk.  reserved[2]: 0 = this form, 1 / 2 = rotate-the-chunk kernel (block spectrum
     // in shared memory / registers), kept as comparison variants.  More than 16 masks keep the rotate kernel (the
     // bin's spectra would not leave room for four CTAs per SM).
     if (h->cfg.reserved[2] == 0 && M <= 16) {
-        if (int rc = dev_alloc(h, &h->d_xbs, (size_t)h->nblk256 * 128)) return rc;
+        if (int rc = alloc_fs256_lane(h, 0)) return rc;
         if (int rc = dev_alloc(h, &h->d_gs, (size_t)D * M * 128)) return rc;
         const long long n = (long long)D * M * 128;
         shifted_filters256_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_masks, h->d_shifts, h->d_gs, N, D, M);
@@ -468,7 +480,15 @@ static int plan_fast256(pcs_handle* h, const float* masks_host) {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->fs_items = h->cfg.reserved[1] >> 8;      // 0 = choose per launch
         h->fs256 = true;
+        return 0;
     }
+    if (int rc = dev_alloc(h, &h->d_psum256, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_pmax256, np)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_sum, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_max, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_part_blk, (size_t)PCS_RED_SLICES * D * M)) return rc;
+    if (int rc = dev_alloc(h, &h->d_done, (size_t)1)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
     return 0;
 }
 
@@ -510,6 +530,8 @@ extern "C" {
 const char* pcs_last_error(void) { return g_last_error.c_str(); }
 int pcs_abi_version(void) { return PCS_ABI_VERSION; }
 
+static void shard_destroy(pcs_handle* h);
+
 int pcs_destroy(pcs_handle* h) {
     if (!h) return PCS_OK;
     cudaSetDevice(h->cfg.device);
@@ -519,12 +541,10 @@ int pcs_destroy(pcs_handle* h) {
     void* pinned[] = {h->h_x, h->h_sigwin, h->h_noisewin, h->h_res, h->h_E, h->h_mag, h->h_sym, h->h_centre, h->h_thr_bits};
     for (void* p : pinned)
         if (p) cudaFreeHost(p);
-    for (int r = 0; r < h->peer_world; ++r)
-        if (h->peer_base[r] && r != h->peer_rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-    if (h->d_xchg) cudaFree(h->d_xchg);
+    shard_destroy(h);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->side) cudaStreamDestroy(h->side);
-    for (cudaEvent_t e : {h->ev_fork, h->ev_est, h->ev_side, h->ev_push})
+    for (cudaEvent_t e : {h->ev_fork, h->ev_est, h->ev_side})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -562,7 +582,6 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_est, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming));
     h->N = N;
     h->logN = ilog2(N);
     h->logN1 = h->logN / 2;
@@ -625,6 +644,7 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
 
     CUDA_TRY(cudaMemcpyAsync(h->d_masks, masks, sizeof(float2) * (size_t)M * N, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_shifts, shifts, sizeof(int) * D, cudaMemcpyHostToDevice, h->stream));
+    h->h_shifts.assign(shifts, shifts + D);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
 
     if (int rc = measure_support(h, &h->Lpos, &h->Lneg)) return rc;
@@ -712,7 +732,23 @@ static int enqueue_spectrum(pcs_handle* h) {
 
 static int enqueue_estimate(pcs_handle* h);
 
-// Search kernel + partial reduction for the handle's bin range [bin_lo, bin_hi).
+// Items (bin, block) per CTA of the shifted-filter search: a multiple of the group count G (a CTA does ceil(items / G)
+// rounds) that minimises rounds x waves, i.e. the time of the slowest SM slot, with a small per-CTA set-up charge
+// (twiddles + the bin's M x 2 KB filter spectra).  Large searches end up near 64; a rank's slice of the bins gets CTAs
+// that still fill whole waves of 4 CTAs per SM.
+static int choose_fs_items(long long items, int G, int sm_count) {
+    const long long slots = 4LL * sm_count;
+    int best = G;
+    double best_cost = 1e300;
+    for (int ipc = 128 / G * G; ipc >= G; ipc -= G) {          // descending: the larger CTA wins ties
+        const long long ctas = (items + ipc - 1) / ipc, waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((double)ipc / G + 0.35);
+        if (cost < best_cost) { best_cost = cost; best = ipc; }
+    }
+    return best;
+}
+
+// Search of the handle's bin range [bin_lo, bin_hi) into the tables tab_E / tab_pv / tab_po (rows bin_lo..bin_hi-1).
 static int enqueue_search_local256(pcs_handle* h) {
     const int Dl = h->bin_hi - h->bin_lo, DM = Dl * h->M;
     const size_t row0 = (size_t)h->bin_lo * h->M;
@@ -726,21 +762,24 @@ static int enqueue_search_local256(pcs_handle* h) {
     p.tw = twp;
     const int Gk = h->cfg.reserved[1] & 0xff;
     if (h->fs256) {
+        // block spectra of the chunk, then ONE kernel: filter products, inverse transforms, |y|^2 sum / max per (bin,
+        // block), and -- by the CTA that completes a bin -- the bin's fixed-order reduction, peak offset, table row and
+        // (bin sharding) the arrival flag in the owner's exchange region
         StageTimer t(h, PCS_STAGE_SEARCH);
-        block_spectra256_kernel<<<(p.nblk + 15) / 16, 256, 0, h->stream>>>(p.x, p.tw, h->d_xbs, p.N, p.nblk, p.V, p.Lpos);
+        pcs_handle::Fs256Bufs& lb = h->fsb[h->cur_lane];
+        block_spectra256_kernel<4><<<(p.nblk + 3) / 4, 64, 0, h->stream>>>(p.x, p.tw, lb.xbs, p.N, p.nblk, p.V, p.Lpos);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
         Fs256Params q{};
-        q.xbs = h->d_xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = p.psum; q.pmax = p.pmax;
+        q.xbs = lb.xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = lb.psum; q.pmax = lb.pmax;
         q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos;
+        q.bin_count = lb.bin_count; q.bins_done = lb.bins_done;
+        q.Efull = h->tab_E + row0; q.peak_val = h->tab_pv + row0; q.peak_off = h->tab_po + row0;
+        q.arrival_flag = h->push_flag; q.arrival_value = h->push_value;
+        h->push_flag = nullptr;       // consumed: the search kernel raises the flag itself
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
-        // items per CTA: 64 amortises the per-CTA set-up (twiddles, the bin's 2 KB x M filter spectra); small searches
-        // (short chunks, a rank's slice of the bins) get smaller CTAs so that the grid still covers >= 2 waves of 4 CTAs
-        // per SM (measured on 32- and 128-bin slices of C2: with chunks in flight 64 beats 8-32 by 3-7 %, for a single
-        // chunk in flight 16-32 is 10 % quicker on the 32-bin slice)
-        q.items_per_cta = h->fs_items > 0 ? h->fs_items
-                                          : (int)std::min<long long>(64, std::max<long long>(G, items / (8LL * h->sm_count) / G * G));
+        q.items_per_cta = h->fs_items > 0 ? h->fs_items : choose_fs_items(items, G, h->sm_count);
         h->search_ctas = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
         const size_t dyn = (size_t)p.M * 128 * sizeof(float4) + (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + dyn);
@@ -756,7 +795,9 @@ static int enqueue_search_local256(pcs_handle* h) {
         kern<<<h->search_ctas, G * 16, dyn, h->stream>>>(q);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
-    } else {
+        return 0;
+    }
+    {
         StageTimer t(h, PCS_STAGE_SEARCH);
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;   // groups per CTA (8: measured best)
@@ -784,9 +825,7 @@ static int enqueue_search_local256(pcs_handle* h) {
     CUDA_TRY(cudaGetLastError());
     peak_locate256_kernel<<<(DM + 15) / 16, 256, 0, h->stream>>>(p, h->d_part_sum, h->d_part_max, h->d_part_blk,
                                                                   h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0,
-                                                                  h->d_done, h->push_flag, h->push_value,
-                                                                  h->fs256 ? h->d_xbs : nullptr,
-                                                                  h->fs256 ? h->d_gs + (size_t)h->bin_lo * h->M * 128 : nullptr);
+                                                                  h->d_done, h->push_flag, h->push_value);
     h->push_flag = nullptr;       // consumed: the locate kernel raises the flag itself
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1221,12 +1260,7 @@ int pcs_fetch(pcs_handle* h, pcs_result* res, float* E_out, int32_t* sym, int32_
         if (int rc = enqueue_fetch_search(h)) return rc;
         if (int rc = enqueue_fetch_demod(h)) return rc;
     }
-    if (h->tail_on_side) {
-        CUDA_TRY(cudaStreamSynchronize(h->side));
-        h->tail_on_side = false;
-    } else {
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->fetch_in_flight = false;
     h->h_res->demod_shift = h->h_res->shift;
     copy_search_out(h, res, E_out);
@@ -1254,21 +1288,25 @@ static float mean_abs(const float2* z, int n) {
 // computeSNR's two window means (dem_base:657-663) for the common geometry in which neither window touches the ends
 // of the spectrum, so that the reference's slices X[a-w : b+w] are exactly the gathered windows.  *ok = 0 otherwise
 // (the caller then evaluates the reference's slicing rules itself).
-int pcs_snr_means(pcs_handle* h, const int32_t* shifts, float* sig_mean, float* noise_mean, int32_t* ok) {
-    if (!h || !shifts || !sig_mean || !noise_mean || !ok) return fail(PCS_ERR_INVALID, "null argument");
-    if (!h->searched) return fail(PCS_ERR_STATE, "pcs_snr_means before a search");
-    const pcs_result* r = reinterpret_cast<const pcs_result*>(h->h_res);
+static void snr_means_from(int N, int w, const int32_t* shifts, const pcs_result* r, const float2* sigwin,
+                           const float2* noisewin, float* sig_mean, float* noise_mean, int32_t* ok) {
     *ok = 0;
-    if (r->status != 0 || r->sig_len <= 0) return PCS_OK;
-    const int N = h->N, w = h->cfg.snr_window;
+    if (r->status != 0 || r->sig_len <= 0) return;
     const int lo = shifts[r->low_idx], hi = shifts[r->high_idx];
     const int nlo = (lo + N / 2) % N, nhi = (hi + N / 2) % N;
     if (!(lo <= hi && nlo <= nhi && lo - w >= 0 && nlo - w >= 0 && hi + w <= N && nhi + w <= N && r->sig_start == lo - w &&
           r->noise_start == nlo - w && r->sig_len == hi - lo + 2 * w && r->noise_len == nhi - nlo + 2 * w))
-        return PCS_OK;
-    *sig_mean = mean_abs(h->h_sigwin, r->sig_len);
-    *noise_mean = mean_abs(h->h_noisewin, r->noise_len);
+        return;
+    *sig_mean = mean_abs(sigwin, r->sig_len);
+    *noise_mean = mean_abs(noisewin, r->noise_len);
     *ok = 1;
+}
+
+int pcs_snr_means(pcs_handle* h, const int32_t* shifts, float* sig_mean, float* noise_mean, int32_t* ok) {
+    if (!h || !shifts || !sig_mean || !noise_mean || !ok) return fail(PCS_ERR_INVALID, "null argument");
+    if (!h->searched) return fail(PCS_ERR_STATE, "pcs_snr_means before a search");
+    snr_means_from(h->N, h->cfg.snr_window, shifts, reinterpret_cast<const pcs_result*>(h->h_res), h->h_sigwin, h->h_noisewin,
+                   sig_mean, noise_mean, ok);
     return PCS_OK;
 }
 
@@ -1456,118 +1494,6 @@ int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod) {
     return PCS_OK;
 }
 
-// ---- bin sharding over NVLink peer memory ------------------------------------------------------------------------
-static size_t xchg_table_bytes(const pcs_handle* h) { return (size_t)h->D * h->M * 4; }
-static size_t xchg_flags_offset(const pcs_handle* h) { return (6 * xchg_table_bytes(h) + 255) / 256 * 256; }
-static float* xchg_table(const pcs_handle* h, unsigned char* base, int parity, int k) {
-    return reinterpret_cast<float*>(base + (size_t)(parity * 3 + k) * xchg_table_bytes(h));
-}
-static unsigned long long* xchg_flags(const pcs_handle* h, unsigned char* base, int parity) {
-    return reinterpret_cast<unsigned long long*>(base + xchg_flags_offset(h)) + parity * 16;
-}
-
-int pcs_peer_export(pcs_handle* h, void* ipc_handle_out) {
-    if (!h || !ipc_handle_out) return fail(PCS_ERR_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (!h->d_xchg) {
-        h->xchg_bytes = xchg_flags_offset(h) + 2 * 16 * sizeof(unsigned long long);
-        CUDA_TRY(cudaMalloc((void**)&h->d_xchg, h->xchg_bytes));      // plain cudaMalloc: CUDA IPC cannot export pooled memory
-        CUDA_TRY(cudaMemset(h->d_xchg, 0, h->xchg_bytes));
-        h->dev_bytes += (int64_t)h->xchg_bytes;
-    }
-    cudaIpcMemHandle_t hd;
-    CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
-    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    memcpy(ipc_handle_out, &hd, sizeof(hd));
-    return PCS_OK;
-}
-
-int pcs_peer_attach(pcs_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
-    if (!h || !ipc_handles) return fail(PCS_ERR_INVALID, "null argument");
-    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(PCS_ERR_INVALID, "bad rank %d / world %d", rank, world);
-    if (!h->d_xchg) return fail(PCS_ERR_STATE, "pcs_peer_attach before pcs_peer_export");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const unsigned char* hs = reinterpret_cast<const unsigned char*>(ipc_handles);
-    for (int r = 0; r < world; ++r) {
-        if (r == rank) { h->peer_base[r] = h->d_xchg; continue; }
-        cudaIpcMemHandle_t hd;
-        memcpy(&hd, hs + (size_t)r * 64, 64);
-        void* p = nullptr;
-        CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_base[r] = reinterpret_cast<unsigned char*>(p);
-    }
-    h->peer_rank = rank;
-    h->peer_world = world;
-    h->peers_attached = true;
-    return PCS_OK;
-}
-
-int pcs_enqueue_search_push(pcs_handle* h, int64_t seq, int32_t owner) {
-    if (!h) return fail(PCS_ERR_INVALID, "null handle");
-    if (!h->peers_attached) return fail(PCS_ERR_STATE, "pcs_enqueue_search_push before pcs_peer_attach");
-    if (!h->uploaded) return fail(PCS_ERR_STATE, "search before upload");
-    if (owner < 0 || owner >= h->peer_world || seq < 0) return fail(PCS_ERR_INVALID, "bad owner %d / seq %lld", owner, (long long)seq);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const int parity = (int)((seq / h->peer_world) & 1);
-    unsigned char* base = h->peer_base[owner];
-    // the search stage stores its rows of the three tables straight into the owner's exchange region (NVLink P2P
-    // stores when the owner is another GPU) ...
-    h->tab_E = xchg_table(h, base, parity, 0);
-    h->tab_pv = xchg_table(h, base, parity, 1);
-    h->tab_po = reinterpret_cast<int*>(xchg_table(h, base, parity, 2));
-    // ... and then raises its arrival flag there: from the last CTA of the locate kernel (256-point path) or from a
-    // one-thread kernel after the reduction (generic path), with a system-scope release
-    h->push_flag = xchg_flags(h, base, parity) + h->peer_rank;
-    h->push_value = (unsigned long long)seq + 1ull;
-    const int rc = enqueue_search_local(h);
-    h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
-    if (rc) { h->push_flag = nullptr; return rc; }
-    if (h->push_flag) {
-        peer_flag_kernel<<<1, 1, 0, h->stream>>>(h->push_flag, h->push_value);
-        h->push_flag = nullptr;
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
-    return PCS_OK;
-}
-
-int pcs_enqueue_owner_tail(pcs_handle* h, int64_t seq) {
-    if (!h) return fail(PCS_ERR_INVALID, "null handle");
-    if (!h->peers_attached) return fail(PCS_ERR_STATE, "pcs_enqueue_owner_tail before pcs_peer_attach");
-    if (!h->uploaded) return fail(PCS_ERR_STATE, "tail before upload");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const int parity = (int)((seq / h->peer_world) & 1);
-    // The tail runs on the handle's second stream so that this rank's next searches do not queue behind it (it mostly
-    // waits for the slowest peer and then runs latency-bound kernels on a few SMs).  It is ordered after this rank's own
-    // push by an event, so the wait kernel below only ever waits for flags written from OTHER GPUs.
-    cudaStream_t main_s = h->stream;
-    if (!h->profiling) {
-        CUDA_TRY(cudaEventRecord(h->ev_push, main_s));
-        CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_push, 0));
-        h->stream = h->side;
-    }
-    int rc = 0;
-    do {
-        peer_wait_kernel<<<1, 32, 0, h->stream>>>(xchg_flags(h, h->d_xchg, parity), h->peer_world,
-                                                  (unsigned long long)seq + 1ull, h->d_res);
-        h->launches++;
-        if (cudaGetLastError() != cudaSuccess) { rc = fail(PCS_ERR_CUDA, "peer_wait_kernel launch failed"); break; }
-        h->tab_E = xchg_table(h, h->d_xchg, parity, 0);
-        h->tab_pv = xchg_table(h, h->d_xchg, parity, 1);
-        h->tab_po = reinterpret_cast<int*>(xchg_table(h, h->d_xchg, parity, 2));
-        rc = enqueue_estimate(h);
-        h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
-        if (rc) break;
-        if ((rc = enqueue_demod(h, -1, false))) break;
-        if ((rc = enqueue_fetch_search(h))) break;
-        if ((rc = enqueue_fetch_demod(h))) break;
-    } while (0);
-    h->tail_on_side = (h->stream == h->side);
-    h->stream = main_s;
-    if (rc) return rc;
-    h->searched = h->demodulated = true;
-    h->fetch_in_flight = true;
-    return PCS_OK;
-}
+#include "shard.inc"
 
 }  // extern "C"

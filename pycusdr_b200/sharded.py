@@ -1,21 +1,25 @@
 """Doppler-bin sharding of the search across GPUs, one process per GPU.
 
-Every rank holds the chunk and the full shift table and searches a contiguous slice of the Doppler bins.  The
-three per-(bin, mask) tables of the slice (energy, peak value, peak offset) are stored by the search kernels
-directly into the exchange region of the chunk's *owner* rank over NVLink peer memory
-(``pcs_enqueue_search_push``); the owner alone then runs the tail of the chunk -- Doppler estimate, demodulation at
-the selected bin, timing recovery, symbol decisions -- on the gathered table, which is the very table a single GPU
+Rank 0 is the ingest rank: it alone receives the radio's samples (one SigFIFO per radio in the reference,
+sigFIFO.py:147-181) and the native engine copies every chunk from its HBM into the peers' chunk rings over NVLink.
+Every rank searches a contiguous slice of the Doppler bins; the three per-(bin, mask) tables of the slice (energy, peak
+value, peak offset) are stored by the search kernel's finishing CTAs directly into the exchange region of the chunk's
+*owner* rank over NVLink peer memory; the owner alone then runs the tail of the chunk -- Doppler estimate, demodulation
+at the selected bin, timing recovery, symbol decisions -- on the gathered table, which is the very table a single GPU
 would have produced, so the results are bit-identical to the unsharded path.  Owners rotate round-robin over the
-chunks, so the part of the work that does not shard costs each rank 1/world of a chunk, and no collective is on
-the per-chunk path.  ``torch.distributed`` (any backend) is used once, to exchange the 64-byte CUDA IPC handles,
-and at the end to gather the per-chunk results on rank 0.
+chunks, so the part of the work that does not shard costs each rank 1/world of a chunk, and no collective is on the
+per-chunk path (``pcs_shard_*`` in include/pycusdr_b200.h; flag protocol in csrc/shard.inc).  ``torch.distributed`` (any
+backend) is used once, to exchange the 64-byte CUDA IPC handles, by the bit post-processing to pass a <= 200-byte carry from
+owner to owner, and at the end to gather the per-chunk results on rank 0.
 
-The classes here are host logic only: they drive an *engine* object with the interface of
-``pycusdr_b200._native.Engine`` (``set_bin_range``, ``peer_export``, ``peer_attach``, ``upload_device``,
-``enqueue_search_push``, ``enqueue_owner_tail``, ``fetch``), which is what lets the world_size-2 ``gloo`` test in
-``tests/test_sharded_cpu.py`` run them without a GPU.
+The classes here are host logic only: they drive an *engine* object with the interface of ``pycusdr_b200._native.Engine``
+(``D``, ``shard_init``, ``shard_attach``, ``shard_host_slot``, ``shard_submit``, ``shard_fetch``), which is what lets the
+world_size-2 ``gloo`` tests in ``tests/test_sharded_cpu.py`` run them without a GPU.
 """
 from collections import deque
+
+SRC_DEVICE, SRC_HOST = 1, 2          # include/pycusdr_b200.h: PCS_SRC_DEVICE / PCS_SRC_HOST
+RESULT_STAGES = 4                    # result stages the engine keeps per owner (csrc/shard.inc: PCS_SHARD_STAGES)
 
 
 def bin_partition(num_bins, world):
@@ -36,99 +40,68 @@ def owner_of(seq, world):
     return seq % world
 
 
-class ShardedSearch:
-    """Per-rank driver. ``all_gather`` is a callable ``obj -> [obj of rank 0, obj of rank 1, ...]`` (e.g. a thin
-    wrapper over ``torch.distributed.all_gather_object``)."""
+class ShardedStream:
+    """Per-rank driver of the native engine.  ``all_gather`` is a callable ``obj -> [obj of rank 0, obj of rank 1, ...]``
+    (e.g. a thin wrapper over ``torch.distributed.all_gather_object``).  ``lag`` = owned chunks kept in flight before the
+    oldest one is collected (at most ``RESULT_STAGES - 1``): collecting late keeps the host off the device's critical
+    path -- by the time chunk ``c`` is fetched, ``lag * world`` later chunks have been enqueued."""
 
-    def __init__(self, engine, rank, world, all_gather):
-        self.engine, self.rank, self.world = engine, rank, world
+    def __init__(self, engine, rank, world, all_gather, ring=0, lag=RESULT_STAGES - 1):
+        if not 0 <= lag < RESULT_STAGES:
+            raise ValueError(f"lag must be in [0, {RESULT_STAGES - 1}]")
+        self.engine, self.rank, self.world, self.lag = engine, rank, world, lag
         self.slices = bin_partition(engine.D, world)
-        lo, hi = self.slices[rank]
-        engine.set_bin_range(lo, hi)
-        handles = all_gather(engine.peer_export())
+        handles = all_gather(engine.shard_init(rank, world, ring))
         if len(handles) != world:
             raise RuntimeError("handle exchange returned %d entries for %d ranks" % (len(handles), world))
-        engine.peer_attach(rank, world, handles)
+        engine.shard_attach(handles)
         self._owned = deque()          # chunks whose tail this rank has enqueued but not collected yet
-        self.results = {}              # seq -> whatever ``collect`` made of engine.fetch()
+        self.results = {}              # seq -> whatever ``collect`` made of engine.shard_fetch(seq)
         self._next_seq = 0
-
-    def enqueue(self, seq, chunk=None, collect=None):
-        """Enqueue chunk ``seq``. ``chunk`` is a device pointer / array understood by the engine, or ``None`` when the
-        samples have been written into the engine's pinned host buffer (``engine.host_buffer``): the H2D copy is then
-        part of the enqueued work, as in ``uploadToGPU`` (dem_base:548-558).  Chunks must come in order.
-        If this rank owns the chunk its tail is enqueued too; the results of the previously owned chunk are collected
-        first (the engine has one result staging area), through ``collect(fetch_tuple)`` if given."""
-        if seq != self._next_seq:
-            raise ValueError(f"chunks must be enqueued in order: expected {self._next_seq}, got {seq}")
-        self._next_seq += 1
-        owner = owner_of(seq, self.world)
-        if owner == self.rank:
-            self.drain(collect)
-        if chunk is None:
-            self.engine.upload()
-        else:
-            self.engine.upload_device(chunk)
-        self.engine.enqueue_search_push(seq, owner)
-        if owner == self.rank:
-            self.engine.enqueue_owner_tail(seq)
-            self._owned.append(seq)
-        return owner
 
     @property
     def next_seq(self):
-        """Sequence number the next ``enqueue`` must carry."""
+        """Sequence number of the chunk the next ``submit`` enqueues."""
         return self._next_seq
 
+    chunks_enqueued = next_seq
+
+    def host_slot(self):
+        """Ingest rank: the pinned buffer (complex64[nfft]) the NEXT chunk's samples are written into before
+        ``submit(kind=SRC_HOST)``; ``None`` on the other ranks."""
+        return self.engine.shard_host_slot(self._next_seq) if self.rank == 0 else None
+
+    def submit(self, src=None, kind=SRC_DEVICE, collect=None):
+        """Enqueue the next chunk on this rank (call on EVERY rank, in the same order).  ``src`` matters on the ingest
+        rank only: a device pointer (``SRC_DEVICE``), a host array (``SRC_HOST``), or ``None`` with ``SRC_HOST`` when the
+        samples were written into ``host_slot()``.  Never waits for another rank; if this rank owns the chunk, owned chunks
+        older than ``lag`` owner rounds are collected first, through ``collect(seq, fetch_tuple)`` if given.  Returns the
+        chunk's owner."""
+        seq = self._next_seq
+        owner = owner_of(seq, self.world)
+        if owner == self.rank:
+            while len(self._owned) > self.lag:
+                self._collect_one(collect)
+        self.engine.shard_submit(seq, kind, src)
+        self._next_seq = seq + 1
+        if owner == self.rank:
+            self._owned.append(seq)
+        return owner
+
+    def _collect_one(self, collect):
+        seq = self._owned.popleft()
+        out = self.engine.shard_fetch(seq)
+        head = out[0] if isinstance(out, tuple) else out
+        if getattr(head, "xchg_timeout", 0):
+            raise RuntimeError(f"chunk {seq}: the exchange failed on rank {self.rank} (code {head.xchg_timeout}: 1 = a "
+                               "peer's rows or the chunk never arrived, 2 = a flag overran); its results are not valid")
+        self.results[seq] = collect(seq, out) if collect is not None else out
+
     def drain(self, collect=None):
-        """Collect the results of every owned chunk still in flight (synchronises with the device)."""
+        """Collect the results of every owned chunk still in flight, in chunk order (synchronises with the device)."""
         while self._owned:
-            seq = self._owned.popleft()
-            out = self.engine.fetch()
-            head = out[0] if isinstance(out, tuple) else out
-            if getattr(head, "xchg_timeout", 0):
-                raise RuntimeError(f"chunk {seq}: a peer's rows never reached rank {self.rank} (exchange timed out); "
-                                   "its results are not valid")
-            self.results[seq] = collect(out) if collect is not None else out
+            self._collect_one(collect)
         return self.results
-
-
-class ShardedPipelines:
-    """``P`` independent ``ShardedSearch`` pipelines per rank (one engine, pair of CUDA streams and exchange region
-    each): chunk ``c`` goes to pipeline ``c % P`` as its local chunk ``c // P``.  With P = 2 the search kernel of one
-    chunk fills the SMs that the last, partially filled wave and the reduction kernels of the previous chunk leave
-    idle -- the same "two chunks in flight" the single-GPU path uses."""
-
-    def __init__(self, engines, rank, world, all_gather):
-        self.pipes = [ShardedSearch(e, rank, world, all_gather) for e in engines]
-        self.rank, self.world = rank, world
-        self.slices = self.pipes[0].slices
-
-    def enqueue(self, chunk_no, chunk=None, collect=None):
-        P = len(self.pipes)
-        return self.pipes[chunk_no % P].enqueue(chunk_no // P, chunk, collect)
-
-    def drain(self, collect=None):
-        """Collect every owned chunk still in flight, in increasing chunk order across the pipelines (each holds at most
-        one).  The order matters to a collector that carries state from chunk to chunk across ranks (OrderedStitcher):
-        pipeline-by-pipeline draining can leave two ranks waiting for each other's carries.  ``collect`` may be one
-        callable or one per pipeline."""
-        P = len(self.pipes)
-        order = sorted((p._owned[0] * P + j, j) for j, p in enumerate(self.pipes) if p._owned)
-        for _, j in order:
-            self.pipes[j].drain(collect[j] if isinstance(collect, (list, tuple)) else collect)
-        return self.results
-
-    @property
-    def chunks_enqueued(self):
-        """Number of chunks enqueued so far = the chunk number the next ``enqueue`` must carry."""
-        return sum(p.next_seq for p in self.pipes)
-
-    @property
-    def results(self):
-        """{global chunk number: result} of the chunks this rank owned."""
-        P = len(self.pipes)
-        return {q * P + j: r for j, p in enumerate(self.pipes) for q, r in p.results.items()}
 
 
 class OrderedStitcher:
@@ -183,63 +156,59 @@ class OrderedStitcher:
 
 
 class ShardedBitStream:
-    """Host samples in, the stitched bit stream out, on N GPUs: ``ShardedPipelines`` for the device work and an
+    """Host samples in on rank 0, the stitched bit stream out, on N GPUs: ``ShardedStream`` for the device work and an
     ``OrderedStitcher`` for the bit post-processing of the chunks this rank owns.
 
-        bs = ShardedBitStream(pipelines, stitcher, rank, world, send, recv, first_chunk=pipelines.chunks_enqueued)
-        for block in blocks:                              # on EVERY rank, the same samples
-            buf = bs.next_buffer()                        # pinned chunk buffer of the pipeline the next chunk goes to
-            buf[:ovl] = previous tail; buf[ovl:] = block  # (after that pipeline's earlier H2D copy has completed)
+        bs = ShardedBitStream(stream, stitcher, rank, world, send, recv)
+        for block in blocks:                              # the loop runs on EVERY rank; only rank 0 touches samples
+            buf = bs.host_slot()                          # rank 0: pinned slot of the next chunk (None elsewhere)
+            if buf is not None:
+                buf[:ovl] = previous tail; buf[ovl:] = block      # demodulator_process.py:287,337
             bs.submit()
         bs.finish()
         bs.bits                                           # {chunk number: (bits, centres, trust)} of the owned chunks
 
-    ``send(token, dst, c)`` / ``recv(src, c)`` move the ≤ 1 KB carry of chunk ``c`` between ranks.  The last chunk's carry
-    is addressed to the owner of a chunk that never comes; ``finish`` takes it off the wire."""
+    ``send(token, dst, c)`` / ``recv(src, c)`` move the carry of chunk ``c`` (<= ``Stitcher.state_capacity`` bytes)
+    between ranks.  The last chunk's carry is addressed to the owner of a chunk that never comes; ``finish`` takes it off
+    the wire."""
 
-    def __init__(self, pipelines, stitcher, rank, world, send, recv, first_chunk=0):
-        self.sh, self.rank, self.world = pipelines, rank, world
-        self.K = len(pipelines.pipes)
-        self.first = self.next = first_chunk
+    def __init__(self, stream, stitcher, rank, world, send, recv, first_chunk=None):
+        self.sh, self.rank, self.world = stream, rank, world
+        self.first = stream.next_seq if first_chunk is None else first_chunk
         self._recv = recv
-        self.ordered = OrderedStitcher(stitcher, rank, self.owner_of_chunk, send, recv, first_chunk)
-        self._owned = [deque() for _ in range(self.K)]
+        self.ordered = OrderedStitcher(stitcher, rank, self.owner_of_chunk, send, recv, self.first)
         self.bits = {}
+        self.info = {}                 # {chunk number: the engine's result block}
 
     def owner_of_chunk(self, c):
-        return owner_of(c // self.K, self.world)          # ShardedPipelines: chunk c = local chunk c // K of pipeline c % K
+        return owner_of(c, self.world)
 
     @property
-    def next_pipe(self):
-        return self.next % self.K
+    def next(self):
+        return self.sh.next_seq
 
-    def next_buffer(self):
-        return self.sh.pipes[self.next_pipe].engine.host_buffer
+    def host_slot(self):
+        return self.sh.host_slot()
 
-    def _collector(self, pipe):
-        def collect(out):
-            c = self._owned[pipe].popleft()
-            res, _, sym, centre, mag = out
-            self.bits[c] = self.ordered(c, sym, centre, mag, (), float(res.sp_sym))
-            return c
-        return collect
+    def _collect(self, c, out):
+        res, sym, centre, mag = out[0], out[2], out[3], out[4]
+        self.info[c] = res
+        self.bits[c] = self.ordered(c, sym, centre, mag, (), float(res.sp_sym))
+        return c
 
-    def submit(self):
-        """The next chunk's samples are in ``next_buffer()``: enqueue it (H2D included).  Returns its chunk number."""
-        c, pipe = self.next, self.next_pipe
-        if self.owner_of_chunk(c) == self.rank:
-            self._owned[pipe].append(c)
-        self.sh.enqueue(c, None, collect=self._collector(pipe))
-        self.next += 1
+    def submit(self, src=None, kind=SRC_HOST):
+        """Enqueue the next chunk (H2D on the ingest rank included).  Returns its chunk number."""
+        c = self.sh.next_seq
+        self.sh.submit(src, kind, collect=self._collect)
         return c
 
     def drain(self):
         """Finish every owned chunk in flight (in chunk order); the stream can go on afterwards."""
-        self.sh.drain([self._collector(j) for j in range(self.K)])
+        self.sh.drain(self._collect)
 
     def finish(self):
         self.drain()
-        last = self.next - 1
+        last = self.sh.next_seq - 1
         if last >= self.first and self.owner_of_chunk(last + 1) == self.rank and self.owner_of_chunk(last) != self.rank:
             self._recv(self.owner_of_chunk(last), last)
         return self.bits

@@ -120,34 +120,28 @@ class _Res:
 
 
 class _StubEngine:
-    """Stands in for ``_native.Engine`` in the host protocol: the "device" returns the symbol table of the chunk whose
-    tail was enqueued (pipeline j of K sees global chunk s * K + j as its local chunk s)."""
+    """Stands in for ``_native.Engine`` in the host protocol: the "device" returns the symbol table of the chunk that is
+    fetched (chunks before ``first`` belong to an earlier, device-resident phase and have no symbols)."""
     D = 64
 
-    def __init__(self, j, K, first, chunks):
-        self.j, self.K, self.first, self.chunks = j, K, first, chunks
-        self.host_buffer = np.zeros(8, np.complex64)
-        self.tail = None
+    def __init__(self, rank, first, chunks):
+        self.rank, self.first, self.chunks = rank, first, chunks
+        self.slot = np.zeros(8, np.complex64)
 
-    def set_bin_range(self, lo, hi): pass
-    def peer_export(self): return b"\0" * 64
-    def peer_attach(self, *a): pass
-    def upload(self): pass
-    def upload_device(self, chunk): pass
-    def enqueue_search_push(self, seq, owner): pass
+    def shard_init(self, rank, world, ring): return b"\0" * 64
+    def shard_attach(self, handles): pass
+    def shard_host_slot(self, seq): return self.slot
+    def shard_submit(self, seq, kind, src): pass
 
-    def enqueue_owner_tail(self, seq):
-        self.tail = seq * self.K + self.j
-
-    def fetch(self):
-        c = self.tail - self.first
+    def shard_fetch(self, seq):
+        c = seq - self.first
         if c < 0:
-            return (_Res(), None, None, None, None)
+            return (_Res(), None, None, None, None, None)
         sym, centre, mag, _, _ = self.chunks[c]
-        return (_Res(), None, sym, centre, mag)
+        return (_Res(), None, sym, centre, mag, None)
 
 
-def _stream_worker(rank, world, port, q, K, prior):
+def _stream_worker(rank, world, port, q, lag, prior):
     import faulthandler
     faulthandler.dump_traceback_later(120, exit=True)       # a protocol deadlock must fail the test, not hang it
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -157,25 +151,28 @@ def _stream_worker(rank, world, port, q, K, prior):
             dist.all_gather_object(out, obj)
             return out
         chunks = [(a, b, c, None, e) for a, b, c, _, e in _chunks()]
-        sh = sharded.ShardedPipelines([_StubEngine(j, K, prior, chunks) for j in range(K)], rank, world, all_gather)
+        sh = sharded.ShardedStream(_StubEngine(rank, prior, chunks), rank, world, all_gather, lag=lag)
         for i in range(prior):                  # device-resident chunks before the host stream starts (as in bench.py)
-            sh.enqueue(i, 1, collect=lambda out: None)
-        sh.drain(lambda out: None)
+            sh.submit(1, sharded.SRC_DEVICE, collect=lambda c, out: None)
+        sh.drain(lambda c, out: None)
         assert sh.chunks_enqueued == prior
         pending = []
+        cap = _native.Stitcher.state_capacity(OVL, 20, SPS // 2, 7)
 
         def send(token, dst, c):
-            buf = torch.zeros(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            assert len(token) <= cap
+            buf = torch.zeros(cap, dtype=torch.uint8)
             buf[:len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
             pending.append(dist.isend(buf, dst=dst, tag=c))
 
         def recv(src, c):
-            buf = torch.empty(_native.Stitcher.STATE_BYTES, dtype=torch.uint8)
+            buf = torch.empty(cap, dtype=torch.uint8)
             dist.recv(buf, src=src, tag=c)
             return buf.numpy().tobytes()
-        bs = sharded.ShardedBitStream(sh, _stitcher(), rank, world, send, recv, first_chunk=prior)
+        bs = sharded.ShardedBitStream(sh, _stitcher(), rank, world, send, recv)
+        assert bs.first == prior
         for k in range(N_CHUNKS):
-            assert bs.next_buffer() is sh.pipes[(prior + k) % K].engine.host_buffer
+            assert (bs.host_slot() is None) == (rank != 0)
             assert bs.submit() == prior + k
             if k == N_CHUNKS // 2:
                 bs.drain()                      # a drain in the middle of the stream must neither block nor lose the carry
@@ -196,15 +193,15 @@ def _stream_worker(rank, world, port, q, K, prior):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("world,K,prior", [(2, 2, 5), (4, 3, 7), (3, 1, 0), (4, 2, 16)])
-def test_host_stream_over_sharded_pipelines_is_exact_and_terminates(world, K, prior):
+@pytest.mark.parametrize("world,lag,prior", [(2, 3, 5), (4, 2, 7), (3, 0, 0), (4, 1, 16)])
+def test_host_stream_over_the_sharded_engine_is_exact_and_terminates(world, lag, prior):
     """``ShardedBitStream``: the whole N > 1 host protocol (what ``bench.py --gpus N`` runs for its e2e figure) with stub
-    engines.  Uneven pipelines (``prior`` not a multiple of K) and K = 3 are the cases in which draining pipeline by
-    pipeline deadlocked on the GPU box in round 1 (ranks waiting for each other's carries)."""
+    engines: owned chunks collected 0..3 owner rounds late, a device-resident phase of any length before the host stream,
+    a drain in the middle.  The carries travel from owner to owner; nobody may wait in a cycle."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, q, K, prior)) for r in range(world)]
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, q, lag, prior)) for r in range(world)]
     for p in procs:
         p.start()
     merged = q.get(timeout=240)

@@ -1,6 +1,6 @@
-"""N > 1 host logic on the CPU: two ``gloo`` ranks drive ``pycusdr_b200.sharded.ShardedSearch`` with a NumPy stand-in
-for the engine (local rows from the oracle, "peer memory" = point-to-point gloo messages to the owner rank).  The merged
-per-chunk results must equal what one process computes over all bins."""
+"""N > 1 host logic on the CPU: two ``gloo`` ranks drive ``pycusdr_b200.sharded.ShardedStream`` with a NumPy stand-in
+for the native engine (chunk "broadcast" from the ingest rank and rows to the owner rank = point-to-point gloo messages,
+local rows from the oracle).  The merged per-chunk results must equal what one process computes over all bins."""
 import os
 import socket
 import sys
@@ -55,67 +55,66 @@ def _tail(orc, E, pv, po, x):
 
 
 class FakeEngine:
-    def __init__(self, rank, world, pipe=0):
-        self.pipe = pipe
+    """NumPy stand-in for ``_native.Engine``'s pcs_shard_* interface: rank 0 "broadcasts" the chunk with gloo messages, every
+    rank computes its rows with the oracle and sends them to the owner, the owner assembles the table when it fetches."""
+
+    def __init__(self, rank, world):
         conf = _conf()
         self.orc = O.OracleDemodulator(conf, protocol_for(conf), RADIO)
         self.D, self.M = len(self.orc.doppCyperSymNorm), self.orc.num_masks
         self.rank, self.world = rank, world
-        self.tables = {}
-        self.out = None
-        self.log = []
-        self.host_buffer = np.zeros(4096, np.complex64)      # stand-in for the pinned chunk buffer
+        self.tables, self.chunks, self.log, self.sends = {}, {}, [], []
+        self.slot = np.zeros(4096, np.complex64)      # stand-in for the pinned host ring
 
-    def set_bin_range(self, lo, hi):
-        self.lo, self.hi = lo, hi
-
-    def peer_export(self):
+    def shard_init(self, rank, world, ring):
+        assert (rank, world) == (self.rank, self.world)
+        self.lo, self.hi = sharded.bin_partition(self.D, world)[rank]
         return bytes([self.rank]) * 64
 
-    def peer_attach(self, rank, world, handles):
-        assert rank == self.rank and world == self.world
-        assert [h[0] for h in handles] == list(range(world)) and all(len(h) == 64 for h in handles)
+    def shard_attach(self, handles):
+        assert [h[0] for h in handles] == list(range(self.world)) and all(len(h) == 64 for h in handles)
 
-    def upload_device(self, chunk):
-        self.x = chunk
+    def shard_host_slot(self, seq):
+        assert self.rank == 0
+        return self.slot
 
-    def upload(self):                       # chunk=None: the samples sit in the engine's pinned host buffer
-        self.x = self.host_buffer.copy()
-
-    def _rows(self):
-        X = O.forward_fft(self.x)
-        return O.search_energy(X, self.orc.masks, self.orc.doppCyperSymNorm[self.lo:self.hi], False, want_peaks=True)
-
-    def enqueue_search_push(self, seq, owner):
-        E, pv, po = self._rows()
+    def shard_submit(self, seq, kind, src):
+        if self.rank == 0:
+            x = self.slot.copy() if src is None else np.asarray(src, dtype=np.complex64)
+            assert kind == (sharded.SRC_HOST if src is None else sharded.SRC_DEVICE)
+            for r in range(1, self.world):
+                self.sends.append(dist.isend(torch.from_numpy(x.view(np.float32).copy()), dst=r, tag=seq * 8 + 7))
+        else:
+            buf = torch.empty(2 * 4096, dtype=torch.float32)
+            dist.recv(buf, src=0, tag=seq * 8 + 7)
+            x = buf.numpy().view(np.complex64)
+        owner = seq % self.world
+        X = O.forward_fft(x)
+        E, pv, po = O.search_energy(X, self.orc.masks, self.orc.doppCyperSymNorm[self.lo:self.hi], False, want_peaks=True)
         self.log.append(("push", seq, owner))
         if owner == self.rank:
             t = self.tables.setdefault(seq, [np.zeros((self.D, self.M), np.float32), np.zeros((self.D, self.M), np.float32),
                                              np.zeros((self.D, self.M), np.int32)])
             t[0][self.lo:self.hi], t[1][self.lo:self.hi], t[2][self.lo:self.hi] = E, pv, po
+            self.chunks[seq] = x
         else:
             for k, a in enumerate((E, pv, po.view(np.float32))):
-                dist.send(torch.from_numpy(np.ascontiguousarray(a)), dst=owner, tag=(seq * 4 + k) * 8 + self.pipe)
+                self.sends.append(dist.isend(torch.from_numpy(np.ascontiguousarray(a)), dst=owner, tag=seq * 8 + k))
 
-    def enqueue_owner_tail(self, seq):
+    def shard_fetch(self, seq):
         t = self.tables.pop(seq)
         for r, (lo, hi) in enumerate(sharded.bin_partition(self.D, self.world)):
             if r == self.rank:
                 continue
             for k in range(3):
                 buf = torch.empty((hi - lo, self.M), dtype=torch.float32)
-                dist.recv(buf, src=r, tag=(seq * 4 + k) * 8 + self.pipe)
+                dist.recv(buf, src=r, tag=seq * 8 + k)
                 t[k][lo:hi] = buf.numpy() if k < 2 else buf.numpy().view(np.int32)
         self.log.append(("tail", seq))
-        self.out = _tail(self.orc, t[0], t[1], t[2], self.x)
-
-    def fetch(self):
-        out, self.out = self.out, None
-        assert out is not None
-        return out
+        return _tail(self.orc, t[0], t[1], t[2], self.chunks.pop(seq))
 
 
-def _worker(rank, world, port, q, pipes=1):
+def _worker(rank, world, port, q, host):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         def all_gather(obj):
@@ -128,22 +127,24 @@ def _worker(rank, world, port, q, pipes=1):
             dist.gather_object(obj, out, dst=0)
             return out
 
-        if pipes == 1:
-            sh = sharded.ShardedSearch(FakeEngine(rank, world), rank, world, all_gather)
-            want_owner = [s % world for s in range(N_CHUNKS)]
-        else:
-            sh = sharded.ShardedPipelines([FakeEngine(rank, world, j) for j in range(pipes)], rank, world, all_gather)
-            want_owner = [(s // pipes) % world for s in range(N_CHUNKS)]
-        if pipes == 1:
-            owners = [sh.enqueue(seq, x) for seq, x in enumerate(_chunks())]
-        else:                               # host-buffer ingestion: samples written into the pipeline's pinned buffer
-            owners = []
-            for seq, x in enumerate(_chunks()):
-                sh.pipes[seq % pipes].engine.host_buffer[:] = x
-                owners.append(sh.enqueue(seq))
+        eng = FakeEngine(rank, world)
+        sh = sharded.ShardedStream(eng, rank, world, all_gather, lag=1)
+        owners = []
+        for seq, x in enumerate(_chunks()):
+            if host:                            # host ingestion: rank 0 writes the samples into the pinned slot
+                slot = sh.host_slot()
+                assert (slot is None) == (rank != 0)
+                if slot is not None:
+                    slot[:] = x
+                owners.append(sh.submit(None, sharded.SRC_HOST))
+            else:                               # only the ingest rank is given the samples
+                owners.append(sh.submit(x if rank == 0 else None, sharded.SRC_DEVICE))
+            assert len(sh._owned) <= 2          # lag = 1: at most the new chunk and one older one in flight
         sh.drain()
-        assert owners == want_owner
-        assert sorted(sh.results) == [s for s in range(N_CHUNKS) if want_owner[s] == rank]
+        for w in eng.sends:
+            w.wait()
+        assert owners == [s % world for s in range(N_CHUNKS)]
+        assert sorted(sh.results) == [s for s in range(N_CHUNKS) if s % world == rank]
         merged = sharded.gather_results(sh.results, world, gather_object, rank)
         if rank == 0:
             q.put([{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in merged])
@@ -167,26 +168,39 @@ def test_bin_partition_and_owner_schedule():
     assert [sharded.owner_of(s, 4) for s in range(6)] == [0, 1, 2, 3, 0, 1]
 
 
-def test_out_of_order_chunks_are_rejected():
+def test_owned_chunks_are_collected_lag_rounds_late():
     class E:
         D = 8
 
-        def set_bin_range(self, lo, hi): pass
-        def peer_export(self): return b"\0" * 64
-        def peer_attach(self, *a): pass
-    sh = sharded.ShardedSearch(E(), 0, 1, lambda o: [o])
+        def __init__(self):
+            self.calls = []
+
+        def shard_init(self, rank, world, ring): return b"\0" * 64
+        def shard_attach(self, handles): pass
+        def shard_submit(self, seq, kind, src): self.calls.append(("submit", seq))
+
+        def shard_fetch(self, seq):
+            self.calls.append(("fetch", seq))
+            return seq
+    e = E()
+    sh = sharded.ShardedStream(e, 0, 1, lambda o: [o], lag=2)
+    for _ in range(5):
+        sh.submit(123)
+    assert e.calls == [("submit", 0), ("submit", 1), ("submit", 2), ("fetch", 0), ("submit", 3), ("fetch", 1), ("submit", 4)]
+    sh.drain()
+    assert sorted(sh.results) == [0, 1, 2, 3, 4] and sh.next_seq == 5
     with pytest.raises(ValueError):
-        sh.enqueue(1, None)
+        sharded.ShardedStream(E(), 0, 1, lambda o: [o], lag=sharded.RESULT_STAGES)
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("pipes", [1, 2])
-def test_two_gloo_ranks_reproduce_the_single_process_result(pipes):
+@pytest.mark.parametrize("host", [False, True])
+def test_two_gloo_ranks_reproduce_the_single_process_result(host):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, pipes)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, host)) for r in range(world)]
     for p in procs:
         p.start()
     merged = q.get(timeout=240)
