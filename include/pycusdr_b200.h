@@ -225,8 +225,9 @@ int pcs_set_stream(pcs_handle* h, uint64_t stream);
 
 /* Per-stage device timing with CUDA events on the handle's stream (bench / roofline reporting).
  * Stages: 0 chunk spectrum, 1 search kernel, 2 estimate, 3 demod surface, 4 timing + symbols,
- * 5 partial reduction.  pcs_get_profile fills double[6] accumulated milliseconds and int64[6] counts. */
-#define PCS_NUM_STAGES 6
+ * 5 partial reduction (search forms without the fused finish), 6 block spectra of the chunk.
+ * pcs_get_profile fills double[7] accumulated milliseconds and int64[7] counts. */
+#define PCS_NUM_STAGES 7
 int pcs_set_profiling(pcs_handle* h, int enable);
 int pcs_get_profile(pcs_handle* h, double* stage_ms, int64_t* stage_count);
 

@@ -128,6 +128,8 @@ class RefGpuDemodulator:
         self.dopplerIdxlast = 0
         self.last = {}
         self.launches = 0
+        self.inspect = True      # keep E[D,M] of every chunk in .last (one extra D2H the reference does not do; the timed
+                                 # reference arm of bench.py switches it off)
 
         # ---- device set-up: dem_base:177-221 ----
         path = cubin_path(M, self.windowWidth, self.SUM_ALL_MASKS_PYTHON, self.CODE_SEARCH_MASK_OFFSET)
@@ -341,7 +343,9 @@ class RefGpuDemodulator:
             return 0, 0, self.clippedPeakIPure, 0
         self.uploadToGPU(samples)
         best = self.search_device()
-        self.last.update(res=best.copy(), E=self.energies())
+        self.last.update(res=best.copy())
+        if self.inspect:
+            self.last.update(E=self.energies())
         try:
             lo, hi, hz, shift = O.interpolate_doppler(best[0], self.doppCyperSymNorm, self.doppHzLUT)
             self.dopplerIdxlast = shift

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpycusdr_b200.so")
+LIB_PATH = os.environ.get("PYCUSDR_B200_LIB") or os.path.join(_HERE, "libpycusdr_b200.so")     # (env: kernel experiments)
 ABI_VERSION = 1
 
 PATH_AUTO, PATH_OVERLAP_SAVE, PATH_FULL, PATH_PARSEVAL = 0, 1, 2, 3
@@ -594,7 +594,7 @@ class Engine:
     def set_stream(self, stream_ptr):
         self._check(self.lib.pcs_set_stream(self._h, int(stream_ptr)))
 
-    STAGES = ("spectrum", "search", "estimate", "demod_surface", "timing_symbols", "reduce")
+    STAGES = ("spectrum", "search", "estimate", "demod_surface", "timing_symbols", "reduce", "block_spectra")
 
     def set_profiling(self, enable=True):
         self._check(self.lib.pcs_set_profiling(self._h, int(bool(enable))))

@@ -11,9 +11,9 @@ namespace pcs {
 // Result block written by the device and copied to pinned host memory once per chunk.
 // ---------------------------------------------------------------------------------------------
 #define PCS_WINDOW_MAX 8192
-#define PCS_NUM_STAGES 6
+#define PCS_NUM_STAGES 7
 enum { PCS_STAGE_SPECTRUM = 0, PCS_STAGE_SEARCH = 1, PCS_STAGE_ESTIMATE = 2, PCS_STAGE_DEMOD_SURFACE = 3,
-       PCS_STAGE_TIMING_SYMBOLS = 4, PCS_STAGE_REDUCE = 5 };
+       PCS_STAGE_TIMING_SYMBOLS = 4, PCS_STAGE_REDUCE = 5, PCS_STAGE_BLOCK_SPECTRA = 6 };
 struct DevResult {
     float best_idx;      // findDopplerEst res[0]  (kern:562,590)
     float metric_db;     // findDopplerEst res[1]  (kern:565,592)
@@ -430,6 +430,7 @@ struct Fs256Params {
     float* __restrict__ peak_val;       // [D][M]
     int* __restrict__ peak_off;         // [D][M]
     unsigned long long* arrival_flag;   // when non-null: raised (system-scope release) once every bin's rows are stored
+    unsigned long long* ack_flag;       // optional second flag raised with it ("this rank has finished reading the chunk")
     unsigned long long arrival_value;
 };
 
@@ -497,60 +498,83 @@ PCS_DEVINL unsigned fs256_valid_mask(int Lpos, int vlen, int t) {
 
 // Fused finish of one Doppler bin, run by the CTA whose items completed the bin (every thread of the CTA calls it):
 //   1. E[d][m] = 2^-18 * sum over the bin's nblk block partials and the (value, block) of the largest |y|^2, in a fixed
-//      order that depends on nblk only -- 16 interleaved lanes per column (lane j takes blocks j, j + 16, ... in
-//      increasing order), then the 16 lane results in lane order -- so E is bit-identical for every CTA tiling, group count
-//      and bin sharding (kern:421-480 uses float atomics: not reproducible even run to run);
+//      order that depends on nblk only -- 64 interleaved lanes per column (lane j takes blocks j, j + 64, ... in
+//      increasing order), then the 64 lane results in lane order -- so E is bit-identical for every CTA tiling, group count
+//      and bin sharding (kern:421-480 uses float atomics: not reproducible even run to run).  The partials are L2-resident;
+//      what this step costs is L2 latency, so every thread keeps 8 independent 128-bit loads in flight;
 //   2. the offset of the maximum inside the winning block of every mask (lowest sample index wins ties): the block is
 //      recomputed with the bin's filter spectra, which are still in shared memory;
 //   3. the bin's row of the three tables is stored (into the owner's exchange region over NVLink when the search is bin-
 //      sharded), and the CTA that finishes the launch's last bin raises the arrival flag with a system-scope release.
 // No separate reduction / locate / flag kernels remain on the per-chunk path of the shifted-filter search.
-#define PCS_FIN_LANES 16
+#define PCS_FIN_LANES 64
+struct FinAcc {
+    float sum, best;
+    int bb;
+    PCS_DEVINL void init() { sum = 0.f; best = -1.f; bb = 0x7fffffff; }
+    PCS_DEVINL void take(float s, float v, int b) {
+        sum += s;
+        if (v > best) { best = v; bb = b; }
+    }
+};
 template <int G>
 PCS_DEVINL void fs256_finish_bin(const Fs256Params& p, int d, const float4* s_g, float2* buf, const float2* tw,
                                  float (*s_red)[PCS_FIN_LANES][16], int* s_wblk) {
     constexpr int NT = G * 16;
     const int tid = threadIdx.x, t = tid & 15, g = tid >> 4;
-    const int MP = p.M <= 1 ? 1 : p.M <= 2 ? 2 : p.M <= 4 ? 4 : p.M <= 8 ? 8 : 16;     // columns padded to a power of two
-    const int tpc = min(NT / MP, PCS_FIN_LANES), lpt = PCS_FIN_LANES / tpc;              // threads per column, lanes per thread
-    const int m = tid % MP, jt = tid / MP;
-    if (m < p.M && jt < tpc) {
-        const float* __restrict__ ps = p.psum + (size_t)d * p.nblk * p.M + m;
-        const float* __restrict__ pm = p.pmax + (size_t)d * p.nblk * p.M + m;
-        for (int l = 0; l < lpt; ++l) {
-            const int lane = jt * lpt + l;
-            float sum = 0.f, best = -1.f;
-            int bb = 0x7fffffff;
-            int b = lane;
-            constexpr int U = 8, STEP = PCS_FIN_LANES;
-            for (; b + (U - 1) * STEP < p.nblk; b += U * STEP) {       // U independent L2 loads in flight, same summation order
-                float s8[U], v8[U];
+    const int MQ = (p.M + 3) >> 2;                                   // column quads
+    const bool vec = (p.M & 3) == 0;                                 // 128-bit loads need 16-byte aligned rows
+    const float* __restrict__ ps = p.psum + (size_t)d * p.nblk * p.M;
+    const float* __restrict__ pm = p.pmax + (size_t)d * p.nblk * p.M;
+    for (int w = tid; w < PCS_FIN_LANES * MQ; w += NT) {             // work item = (lane, column quad)
+        const int lane = w / MQ, c0 = (w % MQ) * 4;
+        FinAcc a[4];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    s8[u] = __ldcg(ps + (size_t)(b + u * STEP) * p.M);    // written by other SMs in this launch: bypass L1
-                    v8[u] = __ldcg(pm + (size_t)(b + u * STEP) * p.M);
-                }
+        for (int k = 0; k < 4; ++k) a[k].init();
+        constexpr int U = 4, STEP = PCS_FIN_LANES;
+        for (int b = lane; b < p.nblk; b += U * STEP) {
+            float4 s4[U], v4[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    sum += s8[u];
-                    if (v8[u] > best) { best = v8[u]; bb = b + u * STEP; }
+            for (int u = 0; u < U; ++u) {                            // written by other SMs in this launch: bypass L1
+                const int bu = b + u * STEP;
+                s4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v4[u] = make_float4(-1.f, -1.f, -1.f, -1.f);
+                if (bu < p.nblk) {
+                    const size_t o = (size_t)bu * p.M + c0;
+                    if (vec) {
+                        s4[u] = __ldcg(reinterpret_cast<const float4*>(ps + o));
+                        v4[u] = __ldcg(reinterpret_cast<const float4*>(pm + o));
+                    } else {
+                        if (c0 + 0 < p.M) { s4[u].x = __ldcg(ps + o + 0); v4[u].x = __ldcg(pm + o + 0); }
+                        if (c0 + 1 < p.M) { s4[u].y = __ldcg(ps + o + 1); v4[u].y = __ldcg(pm + o + 1); }
+                        if (c0 + 2 < p.M) { s4[u].z = __ldcg(ps + o + 2); v4[u].z = __ldcg(pm + o + 2); }
+                        if (c0 + 3 < p.M) { s4[u].w = __ldcg(ps + o + 3); v4[u].w = __ldcg(pm + o + 3); }
+                    }
                 }
             }
-            for (; b < p.nblk; b += STEP) {
-                sum += __ldcg(ps + (size_t)b * p.M);
-                const float v = __ldcg(pm + (size_t)b * p.M);
-                if (v > best) { best = v; bb = b; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                            // (an absent block adds + 0.0f and never wins the max)
+                const int bu = b + u * STEP;
+                a[0].take(s4[u].x, v4[u].x, bu);
+                a[1].take(s4[u].y, v4[u].y, bu);
+                a[2].take(s4[u].z, v4[u].z, bu);
+                a[3].take(s4[u].w, v4[u].w, bu);
             }
-            s_red[0][lane][m] = sum;
-            s_red[1][lane][m] = best;
-            s_red[2][lane][m] = __int_as_float(bb);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c0 + k < p.M) {
+                s_red[0][lane][c0 + k] = a[k].sum;
+                s_red[1][lane][c0 + k] = a[k].best;
+                s_red[2][lane][c0 + k] = __int_as_float(a[k].bb);
+            }
         }
     }
     __syncthreads();
     if (tid < p.M) {
         float sum = s_red[0][0][tid], best = s_red[1][0][tid];
         int bb = __float_as_int(s_red[2][0][tid]);
-#pragma unroll
+#pragma unroll 8
         for (int l = 1; l < PCS_FIN_LANES; ++l) {
             sum += s_red[0][l][tid];
             const float v = s_red[1][l][tid];
@@ -562,7 +586,7 @@ PCS_DEVINL void fs256_finish_bin(const Fs256Params& p, int d, const float4* s_g,
         p.peak_val[(size_t)d * p.M + tid] = best;
         s_wblk[tid] = bb;
     }
-    __syncthreads();
+    __syncthreads();                               // (also: the lane table is dead before the exchange buffers are reused)
     for (int m0 = 0; m0 < p.M; m0 += G) {          // group g recomputes the winning block of mask m0 + g
         int mm = m0 + g;
         const bool live = mm < p.M;
@@ -608,15 +632,30 @@ PCS_DEVINL void fs256_finish_bin(const Fs256Params& p, int d, const float4* s_g,
             if (p.arrival_flag != nullptr) {
                 __threadfence_system();
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.arrival_flag), "l"(p.arrival_value) : "memory");
+                if (p.ack_flag != nullptr)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.ack_flag), "l"(p.arrival_value) : "memory");
             }
         }
     }
 }
 
-template <int G, int WARPS_PER_SM = 16>     // G = groups (half warps) per CTA; WARPS_PER_SM sets the register budget
-__global__ void __launch_bounds__(G * 16, 2 * WARPS_PER_SM / G) search_fs256_kernel(Fs256Params p) {
+// Register budget of the kernel below.  The mask loop is bound by the FMA pipe and its speed depends on the instruction
+// schedule ptxas finds; measured on C2 (profiles/r02_kernel_variants.md): capped at 112 registers 0.761 ms, at the 128 that
+// __launch_bounds__(128, 4) allows 0.771 ms, at 104 (spills) 0.776 ms, with the finish as a separate function 0.81 ms.
+#ifndef PCS_FS_MAXREG
+#define PCS_FS_MAXREG 112
+#endif
+
+template <int G, int WARPS_PER_SM = 16>     // G = groups (half warps) per CTA; WARPS_PER_SM = 20 is the 96-register tuning build
+__global__ void __maxnreg__(WARPS_PER_SM > 16 ? 96 : PCS_FS_MAXREG) search_fs256_kernel(Fs256Params p) {
+    // the finish's lane table (12 KB) lives in the groups' exchange buffers when they are large enough: the two are never
+    // in use at the same time (every group is past its last transform when a bin is finished)
+    constexpr size_t RED_BYTES = sizeof(float) * 3 * PCS_FIN_LANES * 16;
+    constexpr bool ALIAS = sizeof(float2) * G * 272 >= RED_BYTES;
     __shared__ __align__(16) float2 sbuf[G][272];
-    __shared__ float s_red[3][PCS_FIN_LANES][16];
+    __shared__ __align__(16) float s_red_own[ALIAS ? 4 : 3 * PCS_FIN_LANES * 16];
+    float (*s_red)[PCS_FIN_LANES][16] =
+        reinterpret_cast<float (*)[PCS_FIN_LANES][16]>(ALIAS ? reinterpret_cast<float*>(&sbuf[0][0]) : s_red_own);
     __shared__ int s_wblk[16];
     __shared__ int s_last;
     extern __shared__ float4 s_dyn[];         // [M][128] float4 filter spectra of the current bin | [G][2][M][17] float partials
@@ -1571,11 +1610,11 @@ __global__ void __launch_bounds__(128) threshold_clip_kernel(float2* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 // Peer exchange (bin sharding over NVLink): monotonic 64-bit sequence flags in the ranks' exchange regions, written with
-// system-scope releases by kernels of one GPU and acquired by tiny wait kernels of another.  A wait gives up after ~3 s
+// system-scope releases by kernels of one GPU and acquired by tiny wait kernels of another.  A wait gives up after ~10 s
 // (a peer died) and records it instead of hanging the GPU; a flag NEWER than the one waited for where that cannot
 // legally happen (row flags: the back-pressure of pcs_shard_submit forbids it) is recorded as an overrun.
 // ---------------------------------------------------------------------------------------------
-#define PCS_WAIT_CYCLES 6000000000ll
+#define PCS_WAIT_CYCLES 20000000000ll
 PCS_DEVINL unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1626,6 +1665,54 @@ __global__ void flags_wait_kernel(WaitList w, int exact, int* err, DevResult* re
     if (bad && err) atomicOr(err, bad);
     if (i == 0 && res) res->xchg_timeout = any ? 1 : 0;
     __threadfence_system();
+}
+
+// Ingest rank: chunk `src` -> the own ring slot and the same slot of every peer's ring (NVLink P2P stores), as ONE launch:
+//   prologue  thread 0 of every CTA waits until the slot is free everywhere (the acks in `w`, see csrc/shard.inc)
+//   body      float4 loads of the chunk, one store per destination
+//   epilogue  the CTA that finishes last raises every peer's data flag (system-scope release after the fenced stores)
+struct BcastParams {
+    const float4* __restrict__ src;
+    float4* dst[16];            // dst[0] = own slot (may equal src: then it is skipped), dst[1..n) = peers
+    int ndst;
+    long long n4;               // float4 elements
+    WaitList w;
+    FlagList f;
+    unsigned long long value;
+    unsigned int* done;         // CTA completion counter (self-resetting)
+    int* err;
+};
+__global__ void __launch_bounds__(256) chunk_bcast_kernel(BcastParams p) {
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int i = 0; i < p.w.n; ++i) {
+            if (p.w.want[i] == 0ull) continue;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(p.w.src[i]) < p.w.want[i]) {
+                if (clock64() - t0 > PCS_WAIT_CYCLES) { bad = 1; break; }
+                __nanosleep(100);
+            }
+        }
+        if (bad && p.err) atomicOr(p.err, 1);
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n4; i += stride) {
+        const float4 v = __ldg(p.src + i);
+#pragma unroll 4
+        for (int d = 0; d < p.ndst; ++d)
+            if (p.dst[d] != p.src) p.dst[d][i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *p.done = 0;
+            __threadfence_system();
+            for (int i = 0; i < p.f.n; ++i) st_release_sys(p.f.dst[i], p.value);
+        }
+    }
 }
 
 // computeSNR windows straight from a full spectrum (used when one is available anyway: Parseval variant).

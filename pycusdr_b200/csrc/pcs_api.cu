@@ -76,6 +76,10 @@ struct pcs_handle {
     float *d_ymag = nullptr, *d_p = nullptr, *d_mag = nullptr;
     int *d_sym = nullptr, *d_centre = nullptr;
     DevResult* d_res = nullptr;
+    // d_res | d_E | d_sym | d_centre | d_mag | d_sigwin | d_noisewin live in ONE allocation so that a chunk's results can
+    // leave with a single D2H copy (pcs_shard_*); rb_off[] = byte offsets of the seven parts, rb_bytes = total
+    unsigned char* d_rblock = nullptr;
+    size_t rb_off[7] = {}, rb_bytes = 0;
     // pinned host memory
     float2 *h_x = nullptr, *h_sigwin = nullptr, *h_noisewin = nullptr;
     DevResult* h_res = nullptr;
@@ -120,6 +124,7 @@ struct pcs_handle {
     unsigned int* d_done = nullptr;                       // CTA completion counter of the locate kernel (rotate-form search)
     unsigned long long* push_flag = nullptr;              // when set, the search stage publishes its arrival there
     unsigned long long push_value = 0;
+    unsigned long long* push_ack = nullptr;               // optional second flag raised with push_flag (fused search only)
     float *tab_E = nullptr, *tab_pv = nullptr;   // tables the search stage writes / the estimate stage reads
     int* tab_po = nullptr;
     cudaStream_t side = nullptr;       // forked branch of the graph: chunk spectrum -> SNR bins (off the critical path)
@@ -614,18 +619,29 @@ static int create_impl(pcs_handle* h, const pcs_config* cfg, const int32_t* shif
     if (int rc = dev_alloc(h, &h->d_masks, (size_t)M * N)) return rc;
     if (int rc = dev_alloc(h, &h->d_shifts, (size_t)D)) return rc;
     if (int rc = dev_alloc(h, &h->d_Efull, (size_t)D * M)) return rc;
-    if (int rc = dev_alloc(h, &h->d_E, (size_t)D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_peakv, (size_t)D * M)) return rc;
     if (int rc = dev_alloc(h, &h->d_peako, (size_t)D * M)) return rc;
     h->tab_E = h->d_Efull; h->tab_pv = h->d_peakv; h->tab_po = h->d_peako;
     if (int rc = dev_alloc(h, &h->d_ymag, (size_t)M * N)) return rc;
     if (int rc = dev_alloc(h, &h->d_p, (size_t)N)) return rc;
-    if (int rc = dev_alloc(h, &h->d_sym, (size_t)h->max_sym)) return rc;
-    if (int rc = dev_alloc(h, &h->d_centre, (size_t)h->max_sym)) return rc;
-    if (int rc = dev_alloc(h, &h->d_mag, (size_t)h->max_sym)) return rc;
-    if (int rc = dev_alloc(h, &h->d_sigwin, (size_t)PCS_WINDOW_MAX)) return rc;
-    if (int rc = dev_alloc(h, &h->d_noisewin, (size_t)PCS_WINDOW_MAX)) return rc;
-    if (int rc = dev_alloc(h, &h->d_res, (size_t)1)) return rc;
+    {   // result block: res | E | sym | centre | mag | sigwin | noisewin
+        const size_t sizes[7] = {sizeof(DevResult), sizeof(float) * D * M, sizeof(int) * h->max_sym, sizeof(int) * h->max_sym,
+                                 sizeof(float) * h->max_sym, sizeof(float2) * h->win_cap, sizeof(float2) * h->win_cap};
+        size_t off = 0;
+        for (int i = 0; i < 7; ++i) {
+            h->rb_off[i] = off;
+            off += (sizes[i] + 255) / 256 * 256;
+        }
+        h->rb_bytes = off;
+        if (int rc = dev_alloc(h, &h->d_rblock, off)) return rc;
+        h->d_res = reinterpret_cast<DevResult*>(h->d_rblock + h->rb_off[0]);
+        h->d_E = reinterpret_cast<float*>(h->d_rblock + h->rb_off[1]);
+        h->d_sym = reinterpret_cast<int*>(h->d_rblock + h->rb_off[2]);
+        h->d_centre = reinterpret_cast<int*>(h->d_rblock + h->rb_off[3]);
+        h->d_mag = reinterpret_cast<float*>(h->d_rblock + h->rb_off[4]);
+        h->d_sigwin = reinterpret_cast<float2*>(h->d_rblock + h->rb_off[5]);
+        h->d_noisewin = reinterpret_cast<float2*>(h->d_rblock + h->rb_off[6]);
+    }
     CUDA_TRY(cudaMemsetAsync(h->d_res, 0, sizeof(DevResult), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_sym, 0, sizeof(int) * h->max_sym, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_centre, 0, sizeof(int) * h->max_sym, h->stream));
@@ -765,18 +781,23 @@ static int enqueue_search_local256(pcs_handle* h) {
         // block spectra of the chunk, then ONE kernel: filter products, inverse transforms, |y|^2 sum / max per (bin,
         // block), and -- by the CTA that completes a bin -- the bin's fixed-order reduction, peak offset, table row and
         // (bin sharding) the arrival flag in the owner's exchange region
-        StageTimer t(h, PCS_STAGE_SEARCH);
         pcs_handle::Fs256Bufs& lb = h->fsb[h->cur_lane];
-        block_spectra256_kernel<4><<<(p.nblk + 3) / 4, 64, 0, h->stream>>>(p.x, p.tw, lb.xbs, p.N, p.nblk, p.V, p.Lpos);
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
+        {
+            StageTimer tb(h, PCS_STAGE_BLOCK_SPECTRA);
+            block_spectra256_kernel<4><<<(p.nblk + 3) / 4, 64, 0, h->stream>>>(p.x, p.tw, lb.xbs, p.N, p.nblk, p.V, p.Lpos);
+            h->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        StageTimer t(h, PCS_STAGE_SEARCH);
         Fs256Params q{};
         q.xbs = lb.xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = lb.psum; q.pmax = lb.pmax;
         q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos;
         q.bin_count = lb.bin_count; q.bins_done = lb.bins_done;
         q.Efull = h->tab_E + row0; q.peak_val = h->tab_pv + row0; q.peak_off = h->tab_po + row0;
         q.arrival_flag = h->push_flag; q.arrival_value = h->push_value;
-        h->push_flag = nullptr;       // consumed: the search kernel raises the flag itself
+        q.ack_flag = h->push_flag ? h->push_ack : nullptr;
+        if (h->push_flag) h->push_ack = nullptr;
+        h->push_flag = nullptr;       // consumed: the search kernel raises the flag(s) itself
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
         q.items_per_cta = h->fs_items > 0 ? h->fs_items : choose_fs_items(items, G, h->sm_count);

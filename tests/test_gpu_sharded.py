@@ -74,12 +74,13 @@ def _compare(got, want, what):
             np.testing.assert_array_equal(g[k], w[k], err_msg=f"{what} chunk {c}: {k}")
 
 
-def _run_rank(rank, world, name, kind, all_gather, send, recv, lag=2):
+def _run_rank(rank, world, name, kind, all_gather, send, recv, lag=2, device=0):
     """The per-rank loop of the sharded stream; returns {chunk: result dict} of the chunks this rank owned."""
     import torch
     from pycusdr_b200 import sharded
     from pycusdr_b200.demodulator import UHF
     conf, N, ovl, sig = _case(name)
+    conf["GPU"]["UHF"]["CUDA"]["device"] = device
     step = N - ovl
     dem = UHF.Demodulator(conf, protocol_for(conf), RADIO)
     sh = sharded.ShardedStream(dem._engine, rank, world, all_gather, lag=lag)
@@ -147,7 +148,9 @@ def _worker(rank, world, port, q, name, kind):
     import torch
     import torch.distributed as dist
     from pycusdr_b200 import _native
-    torch.cuda.set_device(0)
+    # PCS_TEST_ONE_GPU_PER_RANK=1 on a multi-GPU box: rank r on cuda:r (NVLink between the ranks); default: all on cuda:0
+    device = rank if (os.environ.get("PCS_TEST_ONE_GPU_PER_RANK") and torch.cuda.device_count() >= world) else 0
+    torch.cuda.set_device(device)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         def all_gather(obj):
@@ -166,7 +169,7 @@ def _worker(rank, world, port, q, name, kind):
             buf = torch.empty(cap, dtype=torch.uint8)
             dist.recv(buf, src=src, tag=c)
             return buf.numpy().tobytes()
-        mine, owned, n = _run_rank(rank, world, name, kind, all_gather, send, recv, lag=1)
+        mine, owned, n = _run_rank(rank, world, name, kind, all_gather, send, recv, lag=1, device=device)
         for w in pending:
             w.wait()
         assert owned == {c for c in range(n) if c % world == rank}
