@@ -549,6 +549,8 @@ def main():
                   "what": "shift, timing bin, symbol count and CRC-32 of the symbol / centre / magnitude tables of every timed "
                           "chunk vs the unsharded path (pcs_enqueue_device + pcs_fetch) on rank 0"}
 
+    barrier()           # nobody submits further chunks while rank 0 is still re-running the timed ones
+
     # ---- per-stage device times: chunks one at a time with CUDA events around every stage ----
     eng.set_profiling(True)
     for _ in range(2 * max(world, 4)):

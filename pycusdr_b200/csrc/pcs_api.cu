@@ -748,12 +748,14 @@ static int enqueue_spectrum(pcs_handle* h) {
 
 static int enqueue_estimate(pcs_handle* h);
 
-// Items (bin, block) per CTA of the shifted-filter search: a multiple of the group count G (a CTA does ceil(items / G)
-// rounds) that minimises rounds x waves, i.e. the time of the slowest SM slot, with a small per-CTA set-up charge
-// (twiddles + the bin's M x 2 KB filter spectra).  Large searches end up near 64; a rank's slice of the bins gets CTAs
-// that still fill whole waves of 4 CTAs per SM.
+// Items (bin, block) per CTA of the shifted-filter search.  Large searches take 64 (measured on C2: 0.761 ms against 0.778 /
+// 0.781 ms for 56 / 112, profiles/r02_kernel_variants.md: CTAs do not run in lockstep waves, so finer CTAs only add set-up).
+// A rank's slice of the bins would leave the last wave mostly empty with that (C2 on 8 GPUs: 628 CTAs on 592 slots), so
+// small searches pick the multiple of the group count G (a CTA does ceil(items / G) rounds) that minimises rounds x waves,
+// with a small per-CTA set-up charge (twiddles + the bin's M x 2 KB filter spectra).
 static int choose_fs_items(long long items, int G, int sm_count) {
     const long long slots = 4LL * sm_count;
+    if (items >= 6 * 64 * slots) return 64;
     int best = G;
     double best_cost = 1e300;
     for (int ipc = 128 / G * G; ipc >= G; ipc -= G) {          // descending: the larger CTA wins ties
