@@ -121,6 +121,15 @@ int pcs_fill_gaps(const int64_t* idx, int32_t n, int32_t min_gap, int64_t* out, 
  * buffer must stay valid until the next synchronising call. */
 int pcs_upload_device(pcs_handle* h, const void* d_chunk);
 
+/* Doppler-RATE hypothesis.  The reference prepares complexHeterodyne (cuda_kernels.cu:755-778,
+ * dem_base:388: out[x] = in[x] * exp(j theta), theta = fmod(((a x) + b) x, 2 pi) + c, fp32) and never calls it; this is the
+ * same statement applied to the uploaded chunk in the time domain.  After the call every pcs_search / pcs_demod /
+ * pcs_process works on the de-chirped chunk, until the next upload or pcs_heterodyne (each call starts again from the chunk
+ * as uploaded; a = b = c = 0 restores it).  A rate search is a loop of pcs_heterodyne + pcs_search over the hypotheses
+ * (a = -pi * rate / fs^2) followed by pcs_heterodyne(best) + pcs_process: `Demodulator.findUHFRates`. */
+int pcs_heterodyne(pcs_handle* h, float a, float b, float c);
+int pcs_get_chunk(pcs_handle* h, float* x_out /* complex64[nfft]: the chunk the search currently works on */);
+
 /* Replaces __findUHF's device part (dem_base:571-605): energy surface reduction, findDopplerEst,
  * shift interpolation (:610-618).  Synchronises.  E_out (float32[(D+off)*M], reference layout) and
  * res may be NULL. */
@@ -290,6 +299,14 @@ int pcs_chunk_to_bits(pcs_handle* h, pcs_stitcher* st, const int32_t* shifts, co
  * increasing order (idx = position in the full convolution; packet start = idx - m + 1); *n_found counts all of them. */
 int pcs_sync_search(const uint8_t* bits, int64_t n, const int8_t* mask, int32_t m, int32_t threshold, int32_t* idx_out,
                     int32_t* score_out, int32_t cap, int32_t* n_found);
+
+/* Soft-combiner bit-stream alignment (softCombiner.py:697-722 with lib/customXCorr.py:5-30), host only, exact integers:
+ * out[k] = sum_j a_pad[(j + k) mod n] * b_pad[j] for k in [0, n): the circular cross-correlation of two 0/1 streams zero
+ * padded to n (the reference: a = the slave's bits, n = 2**ceil(log2(len(a))), b = master[:len(a)]; its
+ * np.abs(customXCorr(...)) equals these integers up to FFT rounding).  n >= na, nb.  pcs_topk_i32 is the reference's
+ * "15 largest by repeated arg-max" (:708-715), first index on ties. */
+int pcs_bit_xcorr(const uint8_t* a, int64_t na, const uint8_t* b, int64_t nb, int64_t n, int32_t* out /* int32[n] */);
+int pcs_topk_i32(const int32_t* v, int64_t n, int32_t k, int64_t* idx_out, int32_t* val_out);
 
 /* Native sample ingest: what the reference's SigFIFO ring buffer (sigFIFO.py:13-181) and the chunk loop of
  * demodulator_process.py:284-338 do on the host, as a pipeline.  Samples are pushed in arbitrary block sizes; every

@@ -454,6 +454,37 @@ def tag_clipped_peaks(trustWin, centresWin, clippedPeakIPure, spSym, Nfft):
 
 
 # --------------------------------------------------------------------------------------
+# Doppler-rate dimension: complexHeterodyne, prepared at dem_base:388 and never called
+# --------------------------------------------------------------------------------------
+def heterodyne(x, a, b=0.0, c=0.0):
+    """out[n] = x[n] * exp(j theta), theta = fmod(((a n) + b) n, 2 pi) + c, everything in float32 (kern:755-778; the
+    (a n) + b is contracted to one fma by nvcc)."""
+    n = np.arange(len(x), dtype=np.float64)
+    ab = (np.float64(F32(a)) * n + np.float64(F32(b))).astype(F32)          # fma(a, n, b): exact in float64, rounded once
+    theta = (ab.astype(np.float64) * n).astype(F32)
+    theta = (np.fmod(theta, F32(2.0) * F32(np.pi)) + F32(c)).astype(F32)
+    w = (np.cos(theta).astype(F32) + 1j * np.sin(theta).astype(F32)).astype(np.complex64)
+    return (np.asarray(x, dtype=np.complex64) * w).astype(np.complex64)
+
+
+def rate_to_a(rate_hz_per_s, fs):
+    """De-chirp coefficient for a linear Doppler rate r [Hz/s]: the signal carries exp(+j pi r t^2) (signals.doppler_rate)."""
+    return F32(-np.pi * float(rate_hz_per_s) / float(fs) ** 2)
+
+
+def search_rates(x, masks, shifts, sum_all_masks, rates_hz_per_s, fs, element_offset=0, workers=1):
+    """One ordinary Doppler search per rate hypothesis on the de-chirped chunk; metric = the largest mask-summed energy.
+    Returns (index of the best rate -- first one on ties --, metrics[rate], E[rate])."""
+    Es, metrics = [], []
+    for r in rates_hz_per_s:
+        X = forward_fft(heterodyne(x, rate_to_a(r, fs)))
+        E = search_energy(X, masks, shifts, sum_all_masks, workers=workers)
+        Es.append(E)
+        metrics.append(float(np.max(np.sum(E[element_offset:], axis=1, dtype=np.float64))))
+    return int(np.argmax(metrics)), np.array(metrics), Es
+
+
+# --------------------------------------------------------------------------------------
 # The whole per-chunk path behind the reference's class contract (SURVEY.md 8(b) B1)
 # --------------------------------------------------------------------------------------
 class OracleDemodulator:

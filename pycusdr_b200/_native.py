@@ -60,6 +60,8 @@ SYMBOLS = {
     "pcs_upload": (C.c_int, [_P]),
     "pcs_upload_thresholded": (C.c_int, [_P, C.c_float, _P, C.c_int32, C.POINTER(C.c_int32), _P]),
     "pcs_upload_device": (C.c_int, [_P, _P]),
+    "pcs_heterodyne": (C.c_int, [_P, C.c_float, C.c_float, C.c_float]),
+    "pcs_get_chunk": (C.c_int, [_P, _P]),
     "pcs_search": (C.c_int, [_P, C.POINTER(Result), _P]),
     "pcs_demod": (C.c_int, [_P, C.c_int32, C.POINTER(Result), _P, _P, _P]),
     "pcs_process": (C.c_int, [_P, C.POINTER(Result), _P, _P, _P, _P]),
@@ -105,6 +107,8 @@ SYMBOLS = {
     "pcs_chunk_to_bits": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(Result), _P, _P, _P, _P, C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.POINTER(C.c_int32), _P, _P, _P, C.POINTER(C.c_int32)]),
     "pcs_sync_search": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
+    "pcs_bit_xcorr": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, _P]),
+    "pcs_topk_i32": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -294,6 +298,41 @@ def sync_search(bits, mask, threshold):
         cap = n.value
 
 
+def bit_xcorr(a, b, n=None):
+    """Exact circular cross-correlation of two 0/1 streams zero padded to ``n`` (default: the reference's
+    ``2**ceil(log2(len(a)))``): ``out[k] = sum_j a[(j + k) % n] * b[j]`` as int32 -- what
+    ``np.abs(customXCorr(a_padded, b))`` (lib/customXCorr.py:5-17) approximates in floating point."""
+    lib = load()
+    a = np.ascontiguousarray(np.asarray(a) != 0, dtype=np.uint8)
+    b = np.ascontiguousarray(np.asarray(b) != 0, dtype=np.uint8)
+    if n is None:
+        n = int(2 ** np.ceil(np.log2(max(len(a), 1))))
+    n = int(n)
+    out = np.empty(n, dtype=np.int32)
+    rc = lib.pcs_bit_xcorr(_ptr(a), len(a), _ptr(b), len(b), n, _ptr(out))
+    if rc != 0:
+        raise NativeError(rc, lib.pcs_last_error().decode())
+    return out
+
+
+def align_bits(slave_bits, master_bits, var_multiplier, n_idx=15):
+    """The soft combiner's alignment test of one slave stream against the master (softCombiner.py:697-722): returns
+    ``(offset, accepted, idx, val, cond)`` -- ``idx`` / ``val`` the ``n_idx`` largest correlation values by repeated
+    arg-max, ``cond = mean(val[2:]) + var_multiplier * std(val[2:])``, ``accepted = val[0] > cond``, ``offset = idx[0]``
+    (where the master's bits start in the slave's)."""
+    lib = load()
+    n = len(slave_bits)
+    corr = bit_xcorr(slave_bits, np.asarray(master_bits)[:n])
+    idx = np.empty(n_idx, dtype=np.int64)
+    val = np.empty(n_idx, dtype=np.int32)
+    rc = lib.pcs_topk_i32(_ptr(corr), len(corr), int(n_idx), _ptr(idx), _ptr(val))
+    if rc != 0:
+        raise NativeError(rc, lib.pcs_last_error().decode())
+    valf = val.astype(np.float64)
+    cond = np.mean(valf[2:]) + var_multiplier * np.std(valf[2:])
+    return int(idx[0]), bool(valf[0] > cond), idx, valf, cond
+
+
 class Ingest:
     """Native sample ingest over several engines (``pcs_ingest_*``): push samples in any block size, pop per-chunk
     results in order.  The engines must share one configuration and outlive this object."""
@@ -424,6 +463,15 @@ class Engine:
 
     def upload_device(self, dev_ptr):
         self._check(self.lib.pcs_upload_device(self._h, _P(dev_ptr)))
+
+    def heterodyne(self, a, b=0.0, c=0.0):
+        """De-chirp the uploaded chunk: x[n] * exp(j (a n^2 + b n + c)) becomes the chunk searched / demodulated next."""
+        self._check(self.lib.pcs_heterodyne(self._h, float(a), float(b), float(c)))
+
+    def chunk(self):
+        x = np.empty(self.nfft, dtype=np.complex64)
+        self._check(self.lib.pcs_get_chunk(self._h, _ptr(x)))
+        return x
 
     def search(self):
         res = Result()

@@ -1725,6 +1725,23 @@ __global__ void spectrum_gather_kernel(const float2* __restrict__ X, int N, cons
     noise_win[i] = X[(res->noise_start + i) & (N - 1)];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Doppler-rate search dimension: the reference prepares `complexHeterodyne` (kern:755-778,
+// dem_base:388) -- out[x] = in[x] * exp(j theta), theta = fmod(((a x) + b) x, 2 pi) + c in fp32 -- and never calls it.
+// Same statement here (fp32 phase, the (a x) + b contraction nvcc makes, accurate sinf / cosf), applied to the chunk in the
+// time domain so that every rate hypothesis is one more pass of the ordinary Doppler search on the de-chirped chunk.
+// ---------------------------------------------------------------------------------------------
+__global__ void heterodyne_kernel(const float2* __restrict__ in, float2* __restrict__ out, float a, float b, float c, int n) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const float xf = (float)x;
+    float theta = __fmul_rn(__fmaf_rn(a, xf, b), xf);
+    theta = fmodf(theta, 2.0f * 3.14159265358979323846f) + c;
+    const float2 w = make_float2(cosf(theta), sinf(theta));
+    const float2 v = in[x];
+    out[x] = make_float2(__fmaf_rn(v.x, w.x, -__fmul_rn(v.y, w.y)), __fmaf_rn(v.x, w.y, __fmul_rn(v.y, w.x)));   // kern:933-940
+}
+
 // fp32 FMA peak probe: 16 independent FMA chains per thread.
 __global__ void fma_peak_kernel(float* sink, int iters, float a, float b) {
     float v[16];

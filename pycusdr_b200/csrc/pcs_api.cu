@@ -69,6 +69,8 @@ struct pcs_handle {
     float2 *d_x = nullptr, *d_X = nullptr, *d_masks = nullptr, *d_gb = nullptr, *d_scratch = nullptr;
     float2 *d_Pf = nullptr, *d_ycplx = nullptr, *d_sigwin = nullptr, *d_noisewin = nullptr;
     const float2* d_x_cur = nullptr;   // chunk source of the current upload (d_x or external)
+    const float2* d_x_base = nullptr;  // the chunk as uploaded (pcs_heterodyne de-chirps it into d_xh and points d_x_cur there)
+    float2* d_xh = nullptr;
     int* d_shifts = nullptr;
     std::vector<int32_t> h_shifts;     // host copy of the shift table (computeSNR window geometry)
     float *d_psum = nullptr, *d_pmax = nullptr, *d_Efull = nullptr, *d_E = nullptr, *d_peakv = nullptr;
@@ -1144,7 +1146,7 @@ int pcs_upload(pcs_handle* h) {
     if (!h) return fail(PCS_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
-    h->d_x_cur = h->d_x;
+    h->d_x_cur = h->d_x_base = h->d_x;
     h->uploaded = true;
     h->searched = h->demodulated = false;
     h->spectrum_pending = true;        // enqueued with the estimate (eager) or on the graph's side branch
@@ -1180,7 +1182,7 @@ int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int
     CUDA_TRY(cudaMemcpyAsync(h->h_thr_bits, h->d_thr_bits, sizeof(unsigned int) * (N / 32), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h_levels, h->d_thr_level, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_x, h->d_x, sizeof(float2) * N, cudaMemcpyDeviceToHost, h->stream));
-    h->d_x_cur = h->d_x;
+    h->d_x_cur = h->d_x_base = h->d_x;
     h->uploaded = true;
     h->searched = h->demodulated = false;
     h->spectrum_pending = true;
@@ -1204,11 +1206,44 @@ int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int
 int pcs_upload_device(pcs_handle* h, const void* d_chunk) {
     if (!h || !d_chunk) return fail(PCS_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    h->d_x_cur = reinterpret_cast<const float2*>(d_chunk);
+    h->d_x_cur = h->d_x_base = reinterpret_cast<const float2*>(d_chunk);
     h->uploaded = true;
     h->searched = h->demodulated = false;
     h->spectrum_pending = true;
     h->spectrum_full = false;
+    return PCS_OK;
+}
+
+// Doppler-rate hypothesis (extension; kern:755-778): the chunk as uploaded, times exp(j (a n^2 + b n + c)), becomes the chunk
+// every following pcs_search / pcs_demod / pcs_process works on, until the next upload or pcs_heterodyne call (each call
+// starts from the chunk as uploaded; a = b = c = 0 restores it without a copy).
+int pcs_heterodyne(pcs_handle* h, float a, float b, float c) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!h->uploaded || !h->d_x_base) return fail(PCS_ERR_STATE, "pcs_heterodyne before pcs_upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->searched = h->demodulated = false;
+    h->spectrum_pending = true;
+    h->spectrum_full = false;
+    if (a == 0.f && b == 0.f && c == 0.f) {
+        h->d_x_cur = h->d_x_base;
+        return PCS_OK;
+    }
+    if (!h->d_xh)
+        if (int rc = dev_alloc(h, &h->d_xh, (size_t)h->N)) return rc;
+    heterodyne_kernel<<<(h->N + 255) / 256, 256, 0, h->stream>>>(h->d_x_base, h->d_xh, a, b, c, h->N);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->d_x_cur = h->d_xh;
+    return PCS_OK;
+}
+
+// The chunk the search currently works on (complex64[nfft]): inspection hook for pcs_heterodyne.
+int pcs_get_chunk(pcs_handle* h, float* x_out) {
+    if (!h || !x_out) return fail(PCS_ERR_INVALID, "null argument");
+    if (!h->uploaded) return fail(PCS_ERR_STATE, "no chunk uploaded");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(x_out, h->d_x_cur, sizeof(float2) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PCS_OK;
 }
 
@@ -1260,7 +1295,7 @@ int pcs_enqueue_device(pcs_handle* h, const void* d_chunk) {
         // graph mode: the captured kernels read the handle's own chunk buffer, so stage the chunk there (one 8N-byte
         // device-to-device copy, ~1 us per MB)
         CUDA_TRY(cudaMemcpyAsync(h->d_x, d_chunk, sizeof(float2) * h->N, cudaMemcpyDeviceToDevice, h->stream));
-        h->d_x_cur = h->d_x;
+        h->d_x_cur = h->d_x_base = h->d_x;
         h->uploaded = true;
         h->spectrum_pending = true;
         h->spectrum_full = false;

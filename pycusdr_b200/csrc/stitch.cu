@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pycusdr_b200.h"
@@ -298,6 +299,83 @@ int pcs_sync_search(const uint8_t* bits, int64_t n, const int8_t* mask, int32_t 
         }
     }
     *n_found = found;
+    return PCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Soft-combiner bit-stream alignment (softCombiner.py:697-722, lib/customXCorr.py:5-30).
+// The reference zero-pads the slave's bits to N = 2^ceil(log2 n), and takes |IFFT(FFT(slave, N) . conj(FFT(master[:n], N)))|:
+// the circular cross-correlation  c[k] = sum_j slave[(j + k) mod N] * master[j]  -- for 0/1 streams the number of positions
+// where both hold a one -- then the 15 largest values by repeated arg-max.  Here c[k] is computed EXACTLY, in integers:
+// 64 bit-rotated copies of the packed slave stream, then popcount(copy_s[(w + q) mod W] & master[w]) for k = 64 q + s.
+// (The reference's values are these integers plus FFT rounding noise; where two shifts hold the same count its arg-max is
+// decided by that noise, here the lowest index wins.)
+// ---------------------------------------------------------------------------------------------------------------------
+int pcs_bit_xcorr(const uint8_t* a, int64_t na, const uint8_t* b, int64_t nb, int64_t n, int32_t* out) {
+    if (!a || !b || !out || na < 0 || nb < 0 || n < 1 || na > n || nb > n) return pcs_fail_msg(PCS_ERR_INVALID, "pcs_bit_xcorr: bad argument");
+    if ((n & 63) != 0) {                                    // short or odd rings: plain sums
+        std::vector<int64_t> ones;
+        for (int64_t j = 0; j < nb; ++j)
+            if (b[j]) ones.push_back(j);
+        for (int64_t k = 0; k < n; ++k) {
+            int32_t c = 0;
+            for (int64_t j : ones) {
+                const int64_t i = (j + k) % n;
+                c += (i < na && a[i]) ? 1 : 0;
+            }
+            out[k] = c;
+        }
+        return PCS_OK;
+    }
+    const int64_t W = n >> 6, Wb = (nb + 63) >> 6;
+    std::vector<uint64_t> A((size_t)W, 0), B((size_t)W, 0);
+    for (int64_t i = 0; i < na; ++i)
+        if (a[i]) A[(size_t)(i >> 6)] |= 1ull << (i & 63);
+    for (int64_t i = 0; i < nb; ++i)
+        if (b[i]) B[(size_t)(i >> 6)] |= 1ull << (i & 63);
+    auto work = [&](int s0, int s1) {
+        std::vector<uint64_t> R((size_t)W);
+        for (int s = s0; s < s1; ++s) {
+            // R bit i = a[(i + s) mod n]
+            for (int64_t w = 0; w < W; ++w)
+                R[(size_t)w] = s ? (A[(size_t)w] >> s) | (A[(size_t)((w + 1) % W)] << (64 - s)) : A[(size_t)w];
+            for (int64_t q = 0; q < W; ++q) {
+                int32_t c = 0;
+                int64_t w2 = q;
+                for (int64_t w = 0; w < Wb; ++w) {
+                    c += __builtin_popcountll(R[(size_t)w2] & B[(size_t)w]);
+                    if (++w2 == W) w2 = 0;
+                }
+                out[64 * q + s] = c;
+            }
+        }
+    };
+    unsigned nt = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (W * Wb < (1 << 14)) nt = 1;                        // small problems: not worth a thread
+    if (nt <= 1) {
+        work(0, 64);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (64 + (int)nt - 1) / (int)nt;
+        for (int s0 = 0; s0 < 64; s0 += per) pool.emplace_back(work, s0, std::min(64, s0 + per));
+        for (auto& t : pool) t.join();
+    }
+    return PCS_OK;
+}
+
+// The k largest entries by repeated arg-max (first index wins ties), as softCombiner.py:708-715 does with
+// `idx[i] = argmax(x); val[i] = x[idx[i]]; x[idx[i]] = 0`.
+int pcs_topk_i32(const int32_t* v, int64_t n, int32_t k, int64_t* idx_out, int32_t* val_out) {
+    if (!v || !idx_out || !val_out || n < 1 || k < 1) return pcs_fail_msg(PCS_ERR_INVALID, "pcs_topk_i32: bad argument");
+    std::vector<int32_t> x(v, v + n);
+    for (int32_t i = 0; i < k; ++i) {
+        int64_t best = 0;
+        for (int64_t j = 1; j < n; ++j)
+            if (x[(size_t)j] > x[(size_t)best]) best = j;
+        idx_out[i] = best;
+        val_out[i] = x[(size_t)best];
+        x[(size_t)best] = 0;
+    }
     return PCS_OK;
 }
 

@@ -226,6 +226,26 @@ class Demodulator:
             self._pending = None
         return self._finish_search(res, E)
 
+    def findUHFRates(self, samples, rates_hz_per_s):
+        """Extension: Doppler-RATE search dimension.  The reference prepares ``complexHeterodyne``
+        (kern:755-778, dem_base:388) and never calls it; here every rate hypothesis de-chirps the uploaded chunk with that
+        kernel's statement (``pcs_heterodyne``, a = -pi r / fs^2) and runs the ordinary Doppler search on it; the hypothesis
+        with the largest mask-summed energy wins (first one on ties), and the chunk stays de-chirped with it for the
+        ``demodulate()`` that follows.  Returns (best rate, metric per rate) + what ``findUHF`` returns."""
+        self.uploadToGPU(samples)
+        eng = self._engine
+        fs = float(self.sampleRate)
+        coeff = [np.float32(-np.pi * float(r) / fs ** 2) for r in rates_hz_per_s]
+        metrics = []
+        for a in coeff:
+            eng.heterodyne(a)
+            res, E = eng.search()
+            metrics.append(float(np.max(np.sum(E[self.doppIdxArrayOffset:], axis=1, dtype=np.float64))))
+        best = int(np.argmax(metrics))
+        eng.heterodyne(coeff[best])
+        self.dopplerRate = float(rates_hz_per_s[best])
+        return (self.dopplerRate, np.array(metrics)) + tuple(self.findUHF())
+
     def _finish_search(self, res, E, wins=None, means=None):
         """Host half of __findUHF (dem_base:604-632) on the device results of one chunk."""
         self.last = {"E": E.copy(), "res": np.array([res.best_idx, res.metric_db], dtype=np.float32),

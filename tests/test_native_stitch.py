@@ -162,3 +162,62 @@ def test_carry_of_a_large_overlap_fits_whatever_the_geometry():
                              bit_lut=np.array([0, 0, 1, 1, 0, 0, 1, 1]), symbol_lut=[])
     other.set_state(token)
     assert other.get_state() == token
+
+
+def _circular_xcorr_exact(a, b, n):
+    """c[k] = sum_j a_pad[(j + k) % n] * b_pad[j] with np.correlate on the doubled ring: exact integers."""
+    ap = np.r_[a, np.zeros(n - len(a))].astype(np.float64)
+    bp = np.asarray(b, dtype=np.float64)
+    ring = np.r_[ap, ap[:max(len(bp) - 1, 0)]]
+    return np.rint(np.correlate(ring, bp, mode="valid")[:n]).astype(np.int32)
+
+
+@pytest.mark.parametrize("n_slave,n_master", [(37, 20), (64, 64), (1000, 400), (5000, 3000), (20000, 2500), (9000, 12000)])
+def test_bit_xcorr_is_the_exact_circular_correlation(n_slave, n_master):
+    """pcs_bit_xcorr (softCombiner.py:697-706 + lib/customXCorr.py:5-17): exact integers, equal to np.correlate on the
+    ring and to the reference's FFT formula up to its floating-point rounding."""
+    rng = np.random.RandomState(n_slave + n_master)
+    slave = rng.randint(0, 2, n_slave).astype(np.uint8)
+    master = rng.randint(0, 2, n_master).astype(np.uint8)
+    m = master[:n_slave]                                   # the reference passes bitsM[:n]
+    got = _native.bit_xcorr(slave, m)
+    n = int(2 ** np.ceil(np.log2(n_slave)))
+    assert got.dtype == np.int32 and len(got) == n
+    np.testing.assert_array_equal(got, _circular_xcorr_exact(slave, m, n))
+    # the reference's own formula: np.abs(ifft(fft(bitsX, N) * conj(fft(bitsM[:n], N)), N)) with bitsX zero padded to N
+    bitsX = np.r_[slave, np.zeros(n - n_slave)]
+    ref = np.abs(np.fft.ifft(np.fft.fft(bitsX, n) * np.conj(np.fft.fft(m, n)), n))
+    assert np.max(np.abs(got - ref)) < 1e-6
+    # odd ring sizes take the plain path
+    got_odd = _native.bit_xcorr(slave, m, n=n_slave + 3)
+    np.testing.assert_array_equal(got_odd, _circular_xcorr_exact(slave, m, n_slave + 3))
+
+
+def test_align_bits_finds_the_masters_position_like_the_reference():
+    """softCombiner.correlate's acceptance test (softCombiner.py:708-722): the master's new bits sit somewhere in the
+    slave's history; idx[0] is where, and val[0] must clear mean + varMultiplier * std of val[2:]."""
+    rng = np.random.RandomState(4)
+    master = rng.randint(0, 2, 3000).astype(np.uint8)
+    for off, ber in ((0, 0.0), (1234, 0.02), (6000, 0.08)):
+        slave = rng.randint(0, 2, 10000).astype(np.uint8)
+        L = min(len(master), len(slave) - off)
+        seg = master[:L].copy()
+        seg[rng.rand(L) < ber] ^= 1
+        slave[off:off + L] = seg
+        pos, ok, idx, val, cond = _native.align_bits(slave, master, 3.0)
+        # the reference's statements on its own (floating point) correlation
+        n = len(slave)
+        N = int(2 ** np.ceil(np.log2(n)))
+        x = np.abs(np.fft.ifft(np.fft.fft(np.r_[slave, np.zeros(N - n)], N) * np.conj(np.fft.fft(master[:n], N)), N))
+        ridx, rval = np.empty(15, int), np.empty(15)
+        for i in range(15):
+            ridx[i] = np.argmax(x)
+            rval[i] = x[ridx[i]]
+            x[ridx[i]] = 0
+        rcond = np.mean(rval[2:]) + 3.0 * np.std(rval[2:])
+        assert (pos, ok) == (off, True) == (int(ridx[0]), bool(rval[0] > rcond))
+        np.testing.assert_allclose(val, rval, atol=1e-6)
+        assert abs(cond - rcond) < 1e-6
+    # unrelated streams are rejected by both
+    pos, ok, idx, val, cond = _native.align_bits(rng.randint(0, 2, 8000), rng.randint(0, 2, 3000), 5.0)
+    assert not ok
