@@ -719,6 +719,19 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baselines(conf, host_chunks[1], budget_s=10.0)
 
+    # ---- labelled comparison variant (north_star): a6-a8 as batched cuFFT with load / store callbacks, same chunk ----
+    variants = {}
+    if world == 1 and not args.no_variants and not args.doppler_bins:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import cufft_variant
+            del dem1, dev_chunks                      # the variant needs up to 1 GiB for its in-place batch buffer
+            torch.cuda.empty_cache()
+            v, _, _ = cufft_variant.run(conf, host_chunks[1], reps=3, bins_per_batch=64)
+            variants["cufft_callback"] = v
+        except Exception as exc:                      # noqa: BLE001  (a comparison variant must not take the line with it)
+            variants["cufft_callback"] = {"unavailable": repr(exc)[:300]}
+
     line = {
         "metric": "doppler_searched_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -738,7 +751,7 @@ def main():
         "value_with_h2d": {"value": value_h2d, "unit": "Msamples/s", "chunks": h2d_chunks,
                            "note": "same loop, every chunk copied from pinned host memory on the ingest rank inside the timed region"},
         "parity_vs_single_gpu": parity["ok"], "parity": parity,
-        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "verify": verify,
+        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "verify": verify, "variants": variants,
     }
     print(json.dumps(line))
     if dist is not None:
