@@ -208,7 +208,7 @@ int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod);
  *   - the owner alone runs estimate + demodulation + timing + symbol decisions on the gathered tables (the very tables one
  *     GPU produces: results are bit-identical to pcs_process) and keeps the results in one of four result stages until
  *     pcs_shard_fetch collects them.
- * pcs_shard_init allocates the exchange region (tables, flags, chunk ring of `ring` slots: even, <= 2 * world, 0 = choose)
+ * pcs_shard_init allocates the exchange region (tables, flags, chunk ring of `ring` slots: even, <= 4 * world, 0 = choose)
  * and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles with any transport and passes them, in rank
  * order, to pcs_shard_attach.  pcs_shard_submit(seq) is then called on EVERY rank for seq = 0, 1, 2, ... (src is ignored
  * on ranks other than 0); it never blocks on another rank.  The owner must fetch chunk seq before it submits chunk
@@ -226,6 +226,9 @@ int pcs_shard_submit(pcs_handle* h, int64_t seq, int32_t src_kind, const void* s
 int pcs_shard_fetch(pcs_handle* h, int64_t seq, pcs_result* res, float* E_out, int32_t* sym, int32_t* centre, float* mag,
                     float* sig_mean, float* noise_mean, int32_t* snr_ok);
 int pcs_shard_sync(pcs_handle* h);
+/* Diagnostic timeline (environment PCS_SHARD_TRACE=1 at pcs_shard_init): for the last <= 64 chunks, milliseconds since init of
+ * {block spectra start, search end, tail end}; out = float[3 * 64]. */
+int pcs_shard_trace(pcs_handle* h, int64_t* first, int32_t* count, float* out);
 int pcs_shard_streams(const pcs_handle* h, uint64_t* out4 /* lane 0, lane 1, copy, tail (cudaStream_t as integers) */);
 
 /* Make the handle enqueue on a caller-owned stream (cudaStream_t as an integer), e.g. the framework

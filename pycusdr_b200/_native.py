@@ -89,6 +89,7 @@ SYMBOLS = {
     "pcs_shard_fetch": (C.c_int, [_P, C.c_int64, C.POINTER(Result), _P, _P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                   C.POINTER(C.c_int32)]),
     "pcs_shard_sync": (C.c_int, [_P]),
+    "pcs_shard_trace": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
     "pcs_shard_streams": (C.c_int, [_P, _P]),
     "pcs_stitch_create": (C.c_int, [C.POINTER(StitchConfig), _P, _P, C.POINTER(_P)]),
     "pcs_stitch_chunk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P, C.POINTER(C.c_int32)]),
@@ -632,6 +633,13 @@ class Engine:
 
     def shard_sync(self):
         self._check(self.lib.pcs_shard_sync(self._h))
+
+    def shard_trace(self):
+        """(first chunk, float32[n, 3]) timeline in ms: block spectra start, search end, tail end (PCS_SHARD_TRACE=1)."""
+        first, n = C.c_int64(0), C.c_int32(0)
+        out = np.zeros((64, 3), dtype=np.float32)
+        self._check(self.lib.pcs_shard_trace(self._h, C.byref(first), C.byref(n), _ptr(out)))
+        return first.value, out[:n.value].copy()
 
     def shard_streams(self):
         """(lane 0, lane 1, copy, tail) CUDA streams of the engine as integers."""

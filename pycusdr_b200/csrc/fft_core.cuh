@@ -98,6 +98,12 @@ __host__ __device__ constexpr int dft_q(int slot) {
     return R == 16 ? ((slot >> 2) + ((slot & 3) << 2)) : R == 8 ? ((slot >> 2) + ((slot & 3) << 1)) : slot;
 }
 
+// slot that holds output q of Dft<R> (inverse of dft_q<R>)
+template <int R>
+__host__ __device__ constexpr int dft_slot(int q) {
+    return R == 16 ? ((q >> 2) + ((q & 3) << 2)) : R == 8 ? ((q >> 1) + ((q & 1) << 2)) : q;
+}
+
 template <int R, int DIR>
 struct Dft;
 
@@ -212,7 +218,25 @@ struct NoPre {
 // One pass. R = radix, LOGNS = log2(Ns).  in: idx -> float2.  out: (idx, float2, slot) where slot is
 // the compile-time register slot (0..15) of that output inside the thread.  pre(v, j) may modify the
 // freshly loaded radix-R vector of butterfly j (used to fuse the Doppler rotation into pass 0).
-template <int LOGB, int R, int LOGNS, int DIR, typename In, typename Out, typename Pre = NoPre>
+// Pass twiddles from a table instead of from powers of w1: PassTw<LOGB>::offset(p) + k * R + r holds
+// exp(-2 pi i k r / (Ns R)) for pass p (Ns = 16^p), r = 0..R-1, k = 0..Ns-1 (built by the host, build_pass_twiddles).
+// One row is R consecutive float2: R/2 128-bit loads that hit L1 replace the log-depth chain of complex multiplies that
+// apply_twiddle_powers needs to generate w^2..w^(R-1) (24 of the 87 complex multiplies of a 2048-point transform, and most of
+// its fixed-latency stalls).
+template <int LOGB>
+struct PassTw {
+    static constexpr int NPASS = (LOGB + 3) / 4;
+    static constexpr int RLAST = 1 << (LOGB - 4 * (NPASS - 1));
+    __host__ __device__ static constexpr int radix(int p) { return p == NPASS - 1 ? RLAST : 16; }
+    __host__ __device__ static constexpr int offset(int p) {      // float2 elements before pass p's table (pass 0 has none)
+        int o = 0;
+        for (int q = 1; q < p; ++q) o += (1 << (4 * q)) * radix(q);
+        return o;
+    }
+    __host__ __device__ static constexpr int total() { return offset(NPASS); }
+};
+
+template <int LOGB, int R, int LOGNS, int DIR, bool TAB = false, typename In, typename Out, typename Pre = NoPre>
 PCS_DEVINL void fft_pass(int t, const float2* __restrict__ tw, In in, Out out, Pre pre = Pre()) {
     constexpr int B = 1 << LOGB, T = B / 16, NB = 16 / R, STR = B / R, NS = 1 << LOGNS;
     constexpr int LOGR = R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
@@ -229,9 +253,21 @@ PCS_DEVINL void fft_pass(int t, const float2* __restrict__ tw, In in, Out out, P
         const int k = j & (NS - 1);
         pre(v[b], j);
         if (LOGNS > 0) {
-            float2 w1 = __ldg(&tw[k * (B / (NS * R))]);   // forward table exp(-2 pi i t / B)
-            if (DIR > 0) w1 = cconj(w1);
-            apply_twiddle_powers<R>(v[b], w1);
+            if (TAB) {                                      // tw = this pass's table
+                const float4* __restrict__ row = reinterpret_cast<const float4*>(tw + (size_t)k * R);
+#pragma unroll
+                for (int rr = 0; rr < R / 2; ++rr) {
+                    const float4 w = __ldg(&row[rr]);
+                    if (rr > 0) v[b][2 * rr] = DIR < 0 ? cmul(v[b][2 * rr], make_float2(w.x, w.y))
+                                                       : cmul(v[b][2 * rr], make_float2(w.x, -w.y));
+                    v[b][2 * rr + 1] = DIR < 0 ? cmul(v[b][2 * rr + 1], make_float2(w.z, w.w))
+                                               : cmul(v[b][2 * rr + 1], make_float2(w.z, -w.w));
+                }
+            } else {
+                float2 w1 = __ldg(&tw[k * (B / (NS * R))]);   // forward table exp(-2 pi i t / B)
+                if (DIR > 0) w1 = cconj(w1);
+                apply_twiddle_powers<R>(v[b], w1);
+            }
         }
         Dft<R, DIR>::run(v[b]);
         const int j0 = ((j >> LOGNS) << (LOGNS + LOGR)) + k;
@@ -246,34 +282,40 @@ PCS_DEVINL void fft_pass(int t, const float2* __restrict__ tw, In in, Out out, P
 // are safe for odd NPASS, and one trailing barrier is added for even NPASS (the last pass then
 // still reads work0 while the next transform's pass 0 would overwrite it).
 // src(idx) supplies natural-order input idx, sink(idx, val, slot) receives natural-order output idx.
-template <int LOGB, int DIR, typename Src, typename Sink, typename Pre = NoPre>
+template <int LOGB, int DIR, bool TAB = false, typename Src, typename Sink, typename Pre = NoPre>
 PCS_DEVINL void group_fft(float2* work0, float2* work1, const float2* __restrict__ tw, int t, int bar_id,
                           Src src, Sink sink, Pre pre = Pre()) {
     using S = FftShape<LOGB>;
+    using P = PassTw<LOGB>;
     auto ld0 = [&](int i) { return work0[padi(i)]; };
     auto ld1 = [&](int i) { return work1[padi(i)]; };
     auto st0 = [&](int i, float2 v, int) { work0[padi(i)] = v; };
     auto st1 = [&](int i, float2 v, int) { work1[padi(i)] = v; };
     static_assert(S::NPASS >= 2 && S::NPASS <= 4, "supported transform sizes: 2^5 .. 2^16");
+    // TAB: tw points at the pass tables (PassTw<LOGB>), else at the forward table exp(-2 pi i t / B)
+    constexpr int O1 = P::offset(1), O2 = P::offset(2), O3 = P::offset(3);
+    const float2* tw1 = TAB ? tw + O1 : tw;
+    const float2* tw2 = TAB ? tw + O2 : tw;
+    const float2* tw3 = TAB ? tw + O3 : tw;
     if constexpr (S::NPASS == 2) {
-        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        fft_pass<LOGB, 16, 0, DIR, false>(t, tw, src, st0, pre);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, S::RLAST, 4, DIR>(t, tw, ld0, sink);
+        fft_pass<LOGB, S::RLAST, 4, DIR, TAB>(t, tw1, ld0, sink);
         group_sync<S::T>(bar_id);
     } else if constexpr (S::NPASS == 3) {
-        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        fft_pass<LOGB, 16, 0, DIR, false>(t, tw, src, st0, pre);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, 16, 4, DIR>(t, tw, ld0, st1);
+        fft_pass<LOGB, 16, 4, DIR, TAB>(t, tw1, ld0, st1);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, S::RLAST, 8, DIR>(t, tw, ld1, sink);
+        fft_pass<LOGB, S::RLAST, 8, DIR, TAB>(t, tw2, ld1, sink);
     } else {
-        fft_pass<LOGB, 16, 0, DIR>(t, tw, src, st0, pre);
+        fft_pass<LOGB, 16, 0, DIR, false>(t, tw, src, st0, pre);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, 16, 4, DIR>(t, tw, ld0, st1);
+        fft_pass<LOGB, 16, 4, DIR, TAB>(t, tw1, ld0, st1);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, 16, 8, DIR>(t, tw, ld1, st0);
+        fft_pass<LOGB, 16, 8, DIR, TAB>(t, tw2, ld1, st0);
         group_sync<S::T>(bar_id);
-        fft_pass<LOGB, S::RLAST, 12, DIR>(t, tw, ld0, sink);
+        fft_pass<LOGB, S::RLAST, 12, DIR, TAB>(t, tw3, ld0, sink);
         group_sync<S::T>(bar_id);
     }
 }

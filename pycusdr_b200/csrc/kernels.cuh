@@ -49,7 +49,9 @@ struct OsSearchParams {
     const int* __restrict__ shifts;     // [D]
     float* __restrict__ psum;           // [D][M][nblk]
     float* __restrict__ pmax;           // [D][M][nblk]
-    int* __restrict__ pidx;             // [D][M][nblk]
+    const int* __restrict__ wblk;       // LOCATE: [D][M] block that holds the largest |y|^2 (from search_reduce_kernel)
+    int* __restrict__ peak_off;         // LOCATE: [D][M] sample offset of that maximum
+    const float2* __restrict__ twp;     // pass twiddle tables (PassTw<LOGB>)
     int N, D, M, nblk, V, Lpos;
     float invN;
     // shifted-filter form (FS = true): block spectra of the unrotated chunk and per-bin filter spectra
@@ -106,10 +108,20 @@ struct RotatePre {
 // FS = true: the shifted-filter form (see search_fs256_kernel): no rotation and no forward transform per item; the
 // block spectrum comes from block_spectra_kernel's table and the filter spectra are the bin's own.  Items are then
 // ordered block-fastest so that the groups of a CTA share the bin's filter spectra in L1.
-template <int LOGB, int G, bool FS>
-__global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSearchParams p) {
+// LOCATE = false: one item = (bin, block), all masks; the epilogue keeps sum |y|^2 and max |y|^2 of the block's valid outputs
+// only (a thread's 16 outputs of the last pass are t + T u, u = 0..15, so validity is a u-range per thread: no index
+// arithmetic per output).  LOCATE = true: one item = (bin, mask): the block search_reduce_kernel found to hold that
+// column's maximum is recomputed once to get the sample offset of the peak (lowest index wins ties).
+#ifndef PCS_OS_MINB
+#define PCS_OS_MINB 2
+#endif
+#ifndef PCS_OS_TAB
+#define PCS_OS_TAB 0      // pass twiddles from tables (fft_core.cuh: PassTw) measured SLOWER on C1: 0.143-0.150 ms against 0.108 ms with
+#endif                 // powers generated in registers (the 8 + 8 128-bit table loads per transform cost more registers than the chain)
+template <int LOGB, int G, bool FS, bool LOCATE>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T <= 256) ? PCS_OS_MINB : 1) search_os_kernel(OsSearchParams p) {
     using S = FftShape<LOGB>;
-    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32, NBUF = 3;
+    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32, NBUF = 3, R = S::RLAST, NB = 16 / R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x / T, t = threadIdx.x % T;
@@ -121,8 +133,19 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSear
     const int bar_id = 1 + g;
 
     const long long item = (long long)blockIdx.x * G + g;
-    if (item >= (long long)p.nblk * p.D) return;      // whole group leaves (own barrier id)
-    const int blk = FS ? (int)(item % p.nblk) : (int)(item / p.D), d = FS ? (int)(item / p.nblk) : (int)(item % p.D);
+    if (item >= (LOCATE ? (long long)p.D * p.M : (long long)p.nblk * p.D)) return;      // whole group leaves (own barrier id)
+    int blk, d, m_lo, m_hi;
+    if (LOCATE) {
+        d = (int)(item / p.M);
+        m_lo = (int)(item % p.M);
+        m_hi = m_lo + 1;
+        blk = min(max(p.wblk[item], 0), p.nblk - 1);
+    } else {
+        blk = FS ? (int)(item % p.nblk) : (int)(item / p.D);
+        d = FS ? (int)(item / p.nblk) : (int)(item % p.D);
+        m_lo = 0;
+        m_hi = p.M;
+    }
     const uint32_t nmask = (uint32_t)p.N - 1u;
     const int n0 = blk * p.V;
 
@@ -148,38 +171,72 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T) search_os_kernel(OsSear
 
     const int vlen = min(p.V, p.N - n0);
     const int lane = t & 31, warp = t >> 5;
-    for (int m = 0; m < p.M; ++m) {
+    // output index of slot (b, s) of the last pass: t + T * u with u = dft_q<R>(s) * NB + b; valid iff Lpos <= index < Lpos + vlen
+    const int ulo = max(0, (p.Lpos - t + T - 1) / T), uhi = min(16, max(0, (p.Lpos + vlen - t + T - 1) / T));
+    const unsigned vm = ulo < uhi ? ((uhi >= 32 ? 0xffffffffu : (1u << uhi) - 1u) & ~((1u << ulo) - 1u)) : 0u;
+    for (int m = m_lo; m < m_hi; ++m) {
         const float2* __restrict__ gm = FS ? p.gs + ((size_t)d * p.M + m) * B : p.gb + (size_t)m * B;
-        PeakAcc acc;
-        acc.init();
         auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
-        auto sink = [&](int i, float2 v, int) {
-            const int rel = i - p.Lpos;
-            if (rel >= 0 && rel < vlen) acc.take(cabs2(v), n0 + rel);
-        };
-        group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
-        acc.warp_reduce();
-        if (lane == 0) {
-            float* r = red + ((size_t)m * NW + warp) * 3;
-            r[0] = acc.sum;
-            r[1] = acc.best;
-            r[2] = __int_as_float(acc.idx);
+        if (LOCATE) {
+            PeakAcc acc;
+            acc.init();
+            auto sink = [&](int i, float2 v, int) {
+                const int rel = i - p.Lpos;
+                if (rel >= 0 && rel < vlen) acc.take(cabs2(v), n0 + rel);
+            };
+            group_fft<LOGB, +1, PCS_OS_TAB != 0>(work0, work1, PCS_OS_TAB ? p.twp : p.tw, t, bar_id, src, sink);
+            acc.warp_reduce();
+            if (lane == 0) {
+                float* r = red + (size_t)warp * 3;
+                r[1] = acc.best;
+                r[2] = __int_as_float(acc.idx);
+            }
+        } else {
+            float mg[16];
+            auto sink = [&](int, float2 v, int slot) { mg[slot] = cabs2(v); };
+            group_fft<LOGB, +1, PCS_OS_TAB != 0>(work0, work1, PCS_OS_TAB ? p.twp : p.tw, t, bar_id, src, sink);
+            float sum = 0.f, best = 0.f;
+#pragma unroll
+            for (int slot = 0; slot < 16; ++slot) {
+                const int u = dft_q<R>(slot % R) * NB + slot / R;
+                const float mv = (vm >> u) & 1u ? mg[slot] : 0.f;
+                sum += mv;
+                best = fmaxf(best, mv);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            }
+            if (lane == 0) {
+                float* r = red + ((size_t)m * NW + warp) * 3;
+                r[0] = sum;
+                r[1] = best;
+            }
         }
     }
     group_sync<T>(bar_id);
-    for (int m = t; m < p.M; m += T) {
-        PeakAcc acc;
-        acc.init();
+    if (LOCATE) {
+        if (t == 0) {
+            PeakAcc acc;
+            acc.init();
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const float* r = red + ((size_t)m * NW + w) * 3;
-            acc.sum += r[0];
-            acc.merge(r[1], __float_as_int(r[2]));
+            for (int w = 0; w < NW; ++w) acc.merge(red[(size_t)w * 3 + 1], __float_as_int(red[(size_t)w * 3 + 2]));
+            p.peak_off[item] = acc.idx == 0x7fffffff ? 0 : acc.idx;
         }
-        const size_t o = ((size_t)d * p.M + m) * p.nblk + blk;
-        p.psum[o] = acc.sum;
-        p.pmax[o] = acc.best;
-        p.pidx[o] = acc.idx;
+    } else {
+        for (int m = t; m < p.M; m += T) {
+            float sum = 0.f, best = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float* r = red + ((size_t)m * NW + w) * 3;
+                sum += r[0];
+                best = fmaxf(best, r[1]);
+            }
+            const size_t o = ((size_t)d * p.M + m) * p.nblk + blk;
+            p.psum[o] = sum;
+            p.pmax[o] = best;
+        }
     }
 }
 
@@ -882,11 +939,11 @@ __global__ void __launch_bounds__(256, 2) peak_locate256_kernel(Os256Params p, c
 
 // ---------------------------------------------------------------------------------------------
 // Reduce the per-block partials (fixed order -> bit-reproducible, unlike the reference's float
-// atomics, kern:463,474).  One warp per (d, m).
+// atomics, kern:463,474).  One warp per (d, m): E, the largest |y|^2 and the block that holds it (lowest block on ties);
+// search_os_kernel<.., LOCATE = true> then turns that block into the peak's sample offset.
 // ---------------------------------------------------------------------------------------------
-__global__ void search_reduce_kernel(const float* __restrict__ psum, const float* __restrict__ pmax,
-                                     const int* __restrict__ pidx, int DM, int nblk, float* __restrict__ Efull,
-                                     float* __restrict__ peak_val, int* __restrict__ peak_off) {
+__global__ void search_reduce_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int DM, int nblk,
+                                     float* __restrict__ Efull, float* __restrict__ peak_val, int* __restrict__ wblk) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= DM) return;
     PeakAcc acc;
@@ -894,13 +951,13 @@ __global__ void search_reduce_kernel(const float* __restrict__ psum, const float
     const size_t base = (size_t)w * nblk;
     for (int b = lane; b < nblk; b += 32) {
         acc.sum += psum[base + b];
-        acc.merge(pmax[base + b], pidx[base + b]);
+        acc.merge(pmax[base + b], b);
     }
     acc.warp_reduce();
     if (lane == 0) {
         Efull[w] = acc.sum * (1.0f / 262144.0f);      // kern:442 (exact power-of-two scale)
         peak_val[w] = acc.best;
-        peak_off[w] = acc.idx;
+        wblk[w] = acc.idx == 0x7fffffff ? 0 : acc.idx;
     }
 }
 

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -63,6 +64,14 @@ struct pcs_handle {
     // large-FFT plan
     int logN1 = 0, logN2 = 0;
     std::map<int, float2*> tw;     // forward twiddle tables by log2 size
+    std::map<int, float2*> twp;    // per-pass twiddle tables (PassTw<LOGB>) by log2 size
+    // working set of one in-flight generic (shared-memory) search: partials, winning blocks, block spectra; a second set lets
+    // two chunks' searches overlap on two streams (pcs_shard_*), cur_lane selects the one the next enqueue uses
+    struct OsBufs {
+        float *psum = nullptr, *pmax = nullptr;   // [D][M][nblk]
+        int* wblk = nullptr;                      // [D][M] block of the largest |y|^2
+        float2* xbs = nullptr;                    // [nblk][B] block spectra (shifted-filter form)
+    } osb[2];
     // device memory
     std::vector<void*> dev_allocs;
     int64_t dev_bytes = 0;
@@ -73,8 +82,8 @@ struct pcs_handle {
     float2* d_xh = nullptr;
     int* d_shifts = nullptr;
     std::vector<int32_t> h_shifts;     // host copy of the shift table (computeSNR window geometry)
-    float *d_psum = nullptr, *d_pmax = nullptr, *d_Efull = nullptr, *d_E = nullptr, *d_peakv = nullptr;
-    int *d_pidx = nullptr, *d_peako = nullptr;
+    float *d_Efull = nullptr, *d_E = nullptr, *d_peakv = nullptr;
+    int* d_peako = nullptr;
     float *d_ymag = nullptr, *d_p = nullptr, *d_mag = nullptr;
     int *d_sym = nullptr, *d_centre = nullptr;
     DevResult* d_res = nullptr;
@@ -95,6 +104,7 @@ struct pcs_handle {
     float4* d_gperm = nullptr;
     float *d_thr_partial = nullptr, *d_thr_level = nullptr;   // pcs_upload_thresholded (allocated on first use)
     unsigned int *d_thr_bits = nullptr, *h_thr_bits = nullptr;
+    bool os_fs = false;                // shifted-filter form of the generic search
     bool fs256 = false;                // shifted-filter form of the 256-point search (block spectra shared by all bins)
     float4* d_gs = nullptr;
     // per-launch working set of the shifted-filter search; a second set lets two chunks' searches overlap on two streams
@@ -105,7 +115,7 @@ struct pcs_handle {
         unsigned int *bin_count = nullptr, *bins_done = nullptr;
     } fsb[2];
     int cur_lane = 0;
-    float2 *d_xbs_os = nullptr, *d_gs_os = nullptr;    // the same for the generic kernel (natural order)
+    float2* d_gs_os = nullptr;         // per-bin filter spectra of the generic kernel's shifted-filter form (natural order)
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;   // rotate-form kernels
     int* d_part_blk = nullptr;
@@ -203,6 +213,44 @@ static int get_twiddles(pcs_handle* h, int logB, const float2** out) {
     return 0;
 }
 
+// Pass tables of the shared-memory transforms (fft_core.cuh: PassTw): for pass p (Ns = 16^p, radix R) the row k holds
+// exp(-2 pi i k r / (Ns R)), r = 0..R-1, in float32 from float64.
+template <int LOGB>
+static void fill_pass_twiddles(std::vector<float2>& host) {
+    using P = PassTw<LOGB>;
+    host.assign((size_t)P::total(), make_float2(1.f, 0.f));
+    for (int p = 1; p < P::NPASS; ++p) {
+        const int Ns = 1 << (4 * p), R = P::radix(p);
+        for (int k = 0; k < Ns; ++k)
+            for (int r = 0; r < R; ++r) {
+                const double a = -2.0 * M_PI * (double)k * (double)r / ((double)Ns * (double)R);
+                host[(size_t)P::offset(p) + (size_t)k * R + r] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
+}
+
+static int get_pass_twiddles(pcs_handle* h, int logB, const float2** out) {
+    auto it = h->twp.find(logB);
+    if (it == h->twp.end()) {
+        std::vector<float2> host;
+        switch (logB) {
+            case 9: fill_pass_twiddles<9>(host); break;
+            case 10: fill_pass_twiddles<10>(host); break;
+            case 11: fill_pass_twiddles<11>(host); break;
+            case 12: fill_pass_twiddles<12>(host); break;
+            case 13: fill_pass_twiddles<13>(host); break;
+            default: return fail(PCS_ERR_INVALID, "no pass twiddles for 2^%d", logB);
+        }
+        float2* d = nullptr;
+        if (int rc = dev_alloc(h, &d, host.size())) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d, host.data(), sizeof(float2) * host.size(), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        it = h->twp.emplace(logB, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 // ---- tiled FFT pass launcher ------------------------------------------------------------------
 template <int LOGB, int DIR, int C, typename Load, typename Store>
 static int launch_tile_t(pcs_handle* h, const TileGeom& g, Load ld, Store st) {
@@ -285,15 +333,24 @@ static int fft_large(pcs_handle* h, Load ld, float2* out) {
 
 // ---- overlap-save launchers ---------------------------------------------------------------------
 template <int LOGB, int G, bool FS>
-static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p) {
+static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p, bool locate) {
     using S = FftShape<LOGB>;
     constexpr int NW = (S::T + 31) / 32, NBUF = 3;
     const size_t smem = (size_t)G * NBUF * S::WORK * sizeof(float2) + (size_t)G * p.M * NW * 3 * sizeof(float);
-    auto kern = search_os_kernel<LOGB, G, FS>;
+    auto kern = search_os_kernel<LOGB, G, FS, false>;
+    auto kloc = search_os_kernel<LOGB, G, FS, true>;
     static size_t configured[PCS_MAX_DEVICES] = {};
     if (configured[h->cfg.device] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kloc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device] = smem;
+    }
+    if (locate) {        // one group per (bin, mask): the peak's sample offset inside the winning block
+        const long long items = (long long)p.D * p.M;
+        kloc<<<(int)((items + G - 1) / G), G * S::T, smem, h->stream>>>(p);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
     if (FS) {      // block spectra of the unrotated chunk, once per chunk
         const size_t bs_smem = (size_t)G * 2 * S::WORK * sizeof(float2);
@@ -303,7 +360,7 @@ static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p) {
             CUDA_TRY(cudaFuncSetAttribute(bs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
             bs_configured[h->cfg.device] = bs_smem;
         }
-        bs<<<(p.nblk + G - 1) / G, G * S::T, bs_smem, h->stream>>>(p.x, p.tw, h->d_xbs_os, p.N, p.nblk, p.V, p.Lpos);
+        bs<<<(p.nblk + G - 1) / G, G * S::T, bs_smem, h->stream>>>(p.x, p.tw, h->osb[h->cur_lane].xbs, p.N, p.nblk, p.V, p.Lpos);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -334,13 +391,13 @@ static int launch_demod_os_t(pcs_handle* h, const OsDemodParams& p) {
     return 0;
 }
 
-static int launch_search_os(pcs_handle* h, const OsSearchParams& p) {
+static int launch_search_os(pcs_handle* h, const OsSearchParams& p, bool locate) {
     switch (h->logB) {
-        case 9: return p.xbs ? launch_search_os_t<9, 8, true>(h, p) : launch_search_os_t<9, 8, false>(h, p);
-        case 10: return p.xbs ? launch_search_os_t<10, 4, true>(h, p) : launch_search_os_t<10, 4, false>(h, p);
-        case 11: return p.xbs ? launch_search_os_t<11, 2, true>(h, p) : launch_search_os_t<11, 2, false>(h, p);
-        case 12: return p.xbs ? launch_search_os_t<12, 1, true>(h, p) : launch_search_os_t<12, 1, false>(h, p);
-        case 13: return p.xbs ? launch_search_os_t<13, 1, true>(h, p) : launch_search_os_t<13, 1, false>(h, p);
+        case 9: return p.xbs ? launch_search_os_t<9, 8, true>(h, p, locate) : launch_search_os_t<9, 8, false>(h, p, locate);
+        case 10: return p.xbs ? launch_search_os_t<10, 4, true>(h, p, locate) : launch_search_os_t<10, 4, false>(h, p, locate);
+        case 11: return p.xbs ? launch_search_os_t<11, 2, true>(h, p, locate) : launch_search_os_t<11, 2, false>(h, p, locate);
+        case 12: return p.xbs ? launch_search_os_t<12, 1, true>(h, p, locate) : launch_search_os_t<12, 1, false>(h, p, locate);
+        case 13: return p.xbs ? launch_search_os_t<13, 1, true>(h, p, locate) : launch_search_os_t<13, 1, false>(h, p, locate);
     }
     return fail(PCS_ERR_INVALID, "unsupported overlap-save block 2^%d", h->logB);
 }
@@ -376,6 +433,19 @@ static int measure_support(pcs_handle* h, int* Lpos, int* Lneg) {
     }
     *Lpos = lp;
     *Lneg = ln;
+    return 0;
+}
+
+// Working set of one in-flight generic search (see pcs_handle::osb).
+static int alloc_os_lane(pcs_handle* h, int lane) {
+    pcs_handle::OsBufs& b = h->osb[lane];
+    if (b.psum) return 0;
+    const size_t np = (size_t)h->D * h->M * h->nblk;
+    if (int rc = dev_alloc(h, &b.psum, np)) return rc;
+    if (int rc = dev_alloc(h, &b.pmax, np)) return rc;
+    if (int rc = dev_alloc(h, &b.wblk, (size_t)h->D * h->M)) return rc;
+    if (h->os_fs)
+        if (int rc = dev_alloc(h, &b.xbs, (size_t)h->nblk << h->logB)) return rc;
     return 0;
 }
 
@@ -415,17 +485,14 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_gb, gb.size())) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->d_gb, gb.data(), sizeof(float2) * gb.size(), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    const size_t np = (size_t)h->D * M * h->nblk;
-    if (int rc = dev_alloc(h, &h->d_psum, np)) return rc;
-    if (int rc = dev_alloc(h, &h->d_pmax, np)) return rc;
-    if (int rc = dev_alloc(h, &h->d_pidx, np)) return rc;
     // Shifted-filter form (see plan_fast256) for the generic kernel, when the 256-point plan will not take the search
     // and the per-bin spectra stay modest (D * M * B * 8 bytes: 8 MiB for CC11xx); reserved[2] != 0 keeps the rotate form.
     const int L256 = 256 - L + 1;
     const bool fast256_will_run = (h->cfg.log2_block == 0 || h->cfg.log2_block == 8) && L256 >= 128 && N >= 4096;
     const size_t gs_elems = (size_t)h->D * M * B;
-    if (h->cfg.reserved[2] == 0 && !fast256_will_run && gs_elems * sizeof(float2) <= ((size_t)256 << 20)) {
-        if (int rc = dev_alloc(h, &h->d_xbs_os, (size_t)h->nblk * B)) return rc;
+    h->os_fs = h->cfg.reserved[2] == 0 && !fast256_will_run && gs_elems * sizeof(float2) <= ((size_t)256 << 20);
+    if (int rc = alloc_os_lane(h, 0)) return rc;
+    if (h->os_fs) {
         if (int rc = dev_alloc(h, &h->d_gs_os, gs_elems)) return rc;
         shifted_filters_kernel<<<(unsigned)((gs_elems + 255) / 256), 256, 0, h->stream>>>(h->d_masks, h->d_shifts, h->d_gs_os, N,
                                                                                           best, h->D, M);
@@ -528,6 +595,41 @@ static int plan_parseval(pcs_handle* h, const float* masks_host) {
     if (int rc = dev_alloc(h, &h->d_PX, (size_t)N)) return rc;
     if (int rc = dev_alloc(h, &h->d_pvpart, (size_t)(N >> 8) * D * std::min(h->pv_mw, 8))) return rc;
     h->parseval = true;
+    return 0;
+}
+
+// Buffers the non-sharded tail of a chunk works in (chunk-spectrum pass 1, demod magnitudes, timing spectrum, result block).
+// The handle owns one set; the streaming engine adds a second one so that the tails of two owned chunks can overlap.
+struct TailSet {
+    float2 *scratch = nullptr, *scratch2 = nullptr, *Pf = nullptr;
+    float *ymag = nullptr, *p = nullptr;
+    unsigned char* rblock = nullptr;
+};
+static void tail_get(const pcs_handle* h, TailSet* t) {
+    t->scratch = h->d_scratch; t->scratch2 = h->d_scratch2; t->Pf = h->d_Pf; t->ymag = h->d_ymag; t->p = h->d_p;
+    t->rblock = h->d_rblock;
+}
+static void tail_set(pcs_handle* h, const TailSet& t) {
+    h->d_scratch = t.scratch; h->d_scratch2 = t.scratch2; h->d_Pf = t.Pf; h->d_ymag = t.ymag; h->d_p = t.p;
+    h->d_rblock = t.rblock;
+    h->d_res = reinterpret_cast<DevResult*>(t.rblock + h->rb_off[0]);
+    h->d_E = reinterpret_cast<float*>(t.rblock + h->rb_off[1]);
+    h->d_sym = reinterpret_cast<int*>(t.rblock + h->rb_off[2]);
+    h->d_centre = reinterpret_cast<int*>(t.rblock + h->rb_off[3]);
+    h->d_mag = reinterpret_cast<float*>(t.rblock + h->rb_off[4]);
+    h->d_sigwin = reinterpret_cast<float2*>(t.rblock + h->rb_off[5]);
+    h->d_noisewin = reinterpret_cast<float2*>(t.rblock + h->rb_off[6]);
+}
+static int tail_alloc(pcs_handle* h, TailSet* t) {
+    const size_t N = (size_t)h->N;
+    if (int rc = dev_alloc(h, &t->scratch, N)) return rc;
+    if (int rc = dev_alloc(h, &t->scratch2, N)) return rc;
+    if (int rc = dev_alloc(h, &t->Pf, N)) return rc;
+    if (int rc = dev_alloc(h, &t->ymag, (size_t)h->M * N)) return rc;
+    if (int rc = dev_alloc(h, &t->p, N)) return rc;
+    if (int rc = dev_alloc(h, &t->rblock, h->rb_bytes)) return rc;
+    CUDA_TRY(cudaMemsetAsync(t->rblock, 0, h->rb_bytes, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -899,26 +1001,29 @@ static int enqueue_search_local(pcs_handle* h) {
     const size_t row0 = (size_t)h->bin_lo * h->M;
     OsSearchParams p{};
     p.x = h->d_x_cur; p.gb = h->d_gb; p.shifts = h->d_shifts + h->bin_lo;
-    p.xbs = h->d_xbs_os;
+    pcs_handle::OsBufs& lb = h->osb[h->cur_lane];
+    p.xbs = lb.xbs;
     p.gs = h->d_gs_os ? h->d_gs_os + ((size_t)row0 << h->logB) : nullptr;
-    p.psum = h->d_psum + row0 * h->nblk; p.pmax = h->d_pmax + row0 * h->nblk; p.pidx = h->d_pidx + row0 * h->nblk;
+    p.psum = lb.psum + row0 * h->nblk; p.pmax = lb.pmax + row0 * h->nblk;
+    p.wblk = lb.wblk + row0; p.peak_off = h->tab_po + row0;
     p.N = h->N; p.D = Dl; p.M = h->M; p.nblk = h->nblk; p.V = h->V; p.Lpos = h->Lpos;
     p.invN = 1.0f / (float)h->N;
     const float2* twp = nullptr;
     if (int rc = get_twiddles(h, h->logB, &twp)) return rc;
     p.tw = twp;
+    if (int rc = get_pass_twiddles(h, h->logB, &twp)) return rc;
+    p.twp = twp;
     {
         StageTimer t(h, PCS_STAGE_SEARCH);
-        if (int rc = launch_search_os(h, p)) return rc;
+        if (int rc = launch_search_os(h, p, false)) return rc;
     }
     StageTimer t2(h, PCS_STAGE_REDUCE);
     const int DM = Dl * h->M;
-    search_reduce_kernel<<<(DM * 32 + 255) / 256, 256, 0, h->stream>>>(p.psum, p.pmax, p.pidx, DM, h->nblk,
-                                                                        h->tab_E + row0, h->tab_pv + row0,
-                                                                        h->tab_po + row0);
+    search_reduce_kernel<<<(DM * 32 + 255) / 256, 256, 0, h->stream>>>(p.psum, p.pmax, DM, h->nblk, h->tab_E + row0,
+                                                                        h->tab_pv + row0, lb.wblk + row0);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    return 0;
+    return launch_search_os(h, p, true);
 }
 
 static int enqueue_search(pcs_handle* h) {
