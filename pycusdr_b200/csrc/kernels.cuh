@@ -1724,15 +1724,20 @@ __global__ void flags_wait_kernel(WaitList w, int exact, int* err, DevResult* re
     __threadfence_system();
 }
 
-// Ingest rank: chunk `src` -> the own ring slot and the same slot of every peer's ring (NVLink P2P stores), as ONE launch:
+// Ingest rank: chunk `src` -> ring slots (own / peers') and, optionally, the chunk's block spectra `src2` -> the peers' block-
+// spectra rings (NVLink P2P stores), as ONE launch:
 //   prologue  thread 0 of every CTA waits until the slot is free everywhere (the acks in `w`, see csrc/shard.inc)
 //   body      float4 loads of the chunk, one store per destination
 //   epilogue  the CTA that finishes last raises every peer's data flag (system-scope release after the fenced stores)
 struct BcastParams {
     const float4* __restrict__ src;
-    float4* dst[16];            // dst[0] = own slot (may equal src: then it is skipped), dst[1..n) = peers
+    float4* dst[16];            // job 1 (the chunk): destinations; one equal to src is skipped
     int ndst;
     long long n4;               // float4 elements
+    const float4* __restrict__ src2;   // job 2 (optional: the chunk's block spectra): same idea
+    float4* dst2[16];
+    int ndst2;
+    long long n4_2;
     WaitList w;
     FlagList f;
     unsigned long long value;
@@ -1754,12 +1759,20 @@ __global__ void __launch_bounds__(256) chunk_bcast_kernel(BcastParams p) {
     }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n4; i += stride) {
-        const float4 v = __ldg(p.src + i);
+    if (p.ndst > 0)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n4; i += stride) {
+            const float4 v = __ldg(p.src + i);
 #pragma unroll 4
-        for (int d = 0; d < p.ndst; ++d)
-            if (p.dst[d] != p.src) p.dst[d][i] = v;
-    }
+            for (int d = 0; d < p.ndst; ++d)
+                if (p.dst[d] != p.src) p.dst[d][i] = v;
+        }
+    if (p.ndst2 > 0)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n4_2; i += stride) {
+            const float4 v = __ldg(p.src2 + i);
+#pragma unroll 4
+            for (int d = 0; d < p.ndst2; ++d)
+                if (p.dst2[d] != p.src2) p.dst2[d][i] = v;
+        }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {

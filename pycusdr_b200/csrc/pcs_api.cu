@@ -115,6 +115,7 @@ struct pcs_handle {
         unsigned int *bin_count = nullptr, *bins_done = nullptr;
     } fsb[2];
     int cur_lane = 0;
+    const float4* xbs_ext = nullptr;   // when set, the next shifted-filter search reads these block spectra instead of computing them
     float2* d_gs_os = nullptr;         // per-bin filter spectra of the generic kernel's shifted-filter form (natural order)
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;   // rotate-form kernels
@@ -888,15 +889,18 @@ static int enqueue_search_local256(pcs_handle* h) {
         // block), and -- by the CTA that completes a bin -- the bin's fixed-order reduction, peak offset, table row and
         // (bin sharding) the arrival flag in the owner's exchange region
         pcs_handle::Fs256Bufs& lb = h->fsb[h->cur_lane];
-        {
+        const float4* xbs = h->xbs_ext;
+        h->xbs_ext = nullptr;
+        if (!xbs) {
             StageTimer tb(h, PCS_STAGE_BLOCK_SPECTRA);
             block_spectra256_kernel<4><<<(p.nblk + 3) / 4, 64, 0, h->stream>>>(p.x, p.tw, lb.xbs, p.N, p.nblk, p.V, p.Lpos);
             h->launches++;
             CUDA_TRY(cudaGetLastError());
+            xbs = lb.xbs;
         }
         StageTimer t(h, PCS_STAGE_SEARCH);
         Fs256Params q{};
-        q.xbs = lb.xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = lb.psum; q.pmax = lb.pmax;
+        q.xbs = xbs; q.gs = h->d_gs + (size_t)h->bin_lo * h->M * 128; q.tw = p.tw; q.psum = lb.psum; q.pmax = lb.pmax;
         q.N = p.N; q.D = Dl; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos;
         q.bin_count = lb.bin_count; q.bins_done = lb.bins_done;
         q.Efull = h->tab_E + row0; q.peak_val = h->tab_pv + row0; q.peak_off = h->tab_po + row0;
@@ -954,6 +958,16 @@ static int enqueue_search_local256(pcs_handle* h) {
                                                                   h->tab_E + row0, h->tab_pv + row0, h->tab_po + row0,
                                                                   h->d_done, h->push_flag, h->push_value);
     h->push_flag = nullptr;       // consumed: the locate kernel raises the flag itself
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Block spectra of chunk `x` into `out` on `stream` (the streaming engine's ingest rank computes them once for every rank).
+static int enqueue_block_spectra256(pcs_handle* h, cudaStream_t stream, const float2* x, float4* out) {
+    const float2* twp = nullptr;
+    if (int rc = get_twiddles(h, 8, &twp)) return rc;
+    block_spectra256_kernel<4><<<(h->nblk256 + 3) / 4, 64, 0, stream>>>(x, twp, out, h->N, h->nblk256, h->V256, h->Lpos);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
