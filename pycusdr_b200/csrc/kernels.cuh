@@ -1744,7 +1744,9 @@ struct BcastParams {
     unsigned int* done;         // CTA completion counter (self-resetting)
     int* err;
 };
-__global__ void __launch_bounds__(256) chunk_bcast_kernel(BcastParams p) {
+// 128-thread CTAs at <= 32 registers: two of them fit on an SM NEXT TO a full complement of search CTAs (4 x 128 threads x 112
+// registers leave 8192 registers and 58 KB of shared memory), so the broadcast never waits for a search wave to retire.
+__global__ void __launch_bounds__(128, 16) chunk_bcast_kernel(BcastParams p) {
     if (threadIdx.x == 0) {
         int bad = 0;
         for (int i = 0; i < p.w.n; ++i) {

@@ -118,6 +118,7 @@ struct pcs_handle {
     const float4* xbs_ext = nullptr;   // when set, the next shifted-filter search reads these block spectra instead of computing them
     float2* d_gs_os = nullptr;         // per-bin filter spectra of the generic kernel's shifted-filter form (natural order)
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
+    int fs_items_cap = 0;              // upper bound for the chosen value (0 = none)
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;   // rotate-form kernels
     int* d_part_blk = nullptr;
     float2* d_scratch2 = nullptr;      // pass-1 output of the timing-recovery transform
@@ -858,12 +859,13 @@ static int enqueue_estimate(pcs_handle* h);
 // A rank's slice of the bins would leave the last wave mostly empty with that (C2 on 8 GPUs: 628 CTAs on 592 slots), so
 // small searches pick the multiple of the group count G (a CTA does ceil(items / G) rounds) that minimises rounds x waves,
 // with a small per-CTA set-up charge (twiddles + the bin's M x 2 KB filter spectra).
-static int choose_fs_items(long long items, int G, int sm_count) {
+static int choose_fs_items(long long items, int G, int sm_count, int cap) {
     const long long slots = 4LL * sm_count;
-    if (items >= 6 * 64 * slots) return 64;
+    if (items >= 6 * 64 * slots && (cap <= 0 || cap >= 64)) return 64;
     int best = G;
     double best_cost = 1e300;
-    for (int ipc = 128 / G * G; ipc >= G; ipc -= G) {          // descending: the larger CTA wins ties
+    const int top = cap > 0 ? std::max(G, std::min(128, cap)) : 128;
+    for (int ipc = top / G * G; ipc >= G; ipc -= G) {          // descending: the larger CTA wins ties
         const long long ctas = (items + ipc - 1) / ipc, waves = (ctas + slots - 1) / slots;
         const double cost = (double)waves * ((double)ipc / G + 0.35);
         if (cost < best_cost) { best_cost = cost; best = ipc; }
@@ -910,7 +912,7 @@ static int enqueue_search_local256(pcs_handle* h) {
         h->push_flag = nullptr;       // consumed: the search kernel raises the flag(s) itself
         const long long items = (long long)p.nblk * Dl;
         const int G = Gk == 16 ? 16 : Gk == 4 ? 4 : 8;
-        q.items_per_cta = h->fs_items > 0 ? h->fs_items : choose_fs_items(items, G, h->sm_count);
+        q.items_per_cta = h->fs_items > 0 ? h->fs_items : choose_fs_items(items, G, h->sm_count, h->fs_items_cap);
         h->search_ctas = (int)((items + q.items_per_cta - 1) / q.items_per_cta);
         const size_t dyn = (size_t)p.M * 128 * sizeof(float4) + (size_t)G * 2 * p.M * 17 * sizeof(float);
         h->search_smem = (int)(G * 272 * sizeof(float2) + dyn);
