@@ -9,8 +9,11 @@ recovery, symbol decisions, result copy to the host.  ``value`` counts the NEW s
 reference's own rate convention, pyCuSDR/demodulator_process.py:333) with the chunks resident in the ingest GPU's HBM
 when the timed region starts; ``value_with_h2d`` is the same loop fed from pinned host memory (SURVEY 8(d): H2D inside);
 ``e2e`` is the metric from host samples to the stitched bit stream through the repo's public API: at N = 1 the
-reference-facing class (``UHF.Demodulator.uploadAndFindCarrier`` + ``demodulate``, strictly alternating, pinned chunk
-buffer), at N > 1 ``sharded.ShardedBitStream`` with ONE ingest rank (rank 0 alone holds host samples).
+reference-facing class (``UHF.Demodulator.uploadAndFindCarrier`` + ``demodulate``, strictly alternating), at N > 1
+``sharded.ShardedBitStream`` with ONE ingest rank (rank 0 alone holds host samples).  In both the samples wait in
+page-locked host memory (a sample ring registered once; chunks are overlapping windows of it) and the H2D copy of every
+chunk is inside the timed region; ``e2e.caller_fill_loop`` is the same figure with the reference's caller unchanged (it
+first copies every block into the one pinned chunk buffer), ``e2e_stream`` the streaming API on one GPU.
 
 Workload (BASELINE.json configs[1]): GMSK 9600 baud x 16 samples/symbol, 2^18-sample chunks,
 256 Doppler bins, 8 matched filters, back-to-back benchmark packets with AWGN at "SNR" 12 dB, seed 2.
@@ -563,36 +566,86 @@ def main():
 
     # ---- end to end: host samples -> stitched bits ----
     e2e = None
+    e2e_stream = None
     verify = None
     e2e_steps = args.e2e_steps or min(args.steps, 12)
     if world == 1 and not args.no_e2e:
         verify = verify_digest(dem1, stream, N, ovl)
-        dem1._stitch.reset()
-        raw = dem1.get_signalBufferHostPointer()
-        raw[:] = 0
-        blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
-        for c in range(min(5, ring)):
-            raw[ovl:] = blocks[c]
-            dem1.uploadAndFindCarrier(raw)
-            dem1.demodulate()
-            raw[:ovl] = raw[-ovl:]
-        torch.cuda.synchronize()
-        nbits = 0
         n_e2e = e2e_steps * cps
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            raw[ovl:] = blocks[(5 + i) % ring]
-            dem1.uploadAndFindCarrier(raw)
-            bits, centres, trust, spSym = dem1.demodulate()
-            nbits += len(bits)
-            raw[:ovl] = raw[-ovl:]
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
         d2h = 88 + 4 * D * M + 12 * eng.max_sym + 2 * 8 * (2 * 5 + 147)
+
+        # (a) the samples sit in a page-locked ring (what a receiver thread fills; chunk c is the window
+        #     [c * step, c * step + N) of it, overlap included) and every call copies its chunk to the GPU from there
+        ext = np.concatenate((np.zeros(ovl, np.complex64), stream))
+        reg = dem1.registerHostMemory(ext)
+        windows = [ext[c * step_samples:c * step_samples + N] for c in range(ring)]
+
+        def loop_ring(first, count):
+            nb = 0
+            for i in range(first, first + count):
+                dem1.uploadAndFindCarrier(windows[i % ring])
+                nb += len(dem1.demodulate()[0])
+            return nb
+
+        # (b) the reference's caller, unchanged (demodulator_process.py:287-337): fill the one pinned chunk buffer, call,
+        #     carry the overlap -- 8 N bytes of host memcpy per chunk on top of (a)
+        raw = dem1.get_signalBufferHostPointer()
+        blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)]
+
+        def loop_fill(first, count):
+            nb = 0
+            for i in range(first, first + count):
+                raw[ovl:] = blocks[i % ring]
+                dem1.uploadAndFindCarrier(raw)
+                nb += len(dem1.demodulate()[0])
+                raw[:ovl] = raw[-ovl:]
+            return nb
+
+        def timed_loop(loop):
+            dem1._stitch.reset()
+            raw[:] = 0
+            loop(0, min(5, ring))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nb = loop(5, n_e2e)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, nb
+        dt_fill, nbits_fill = timed_loop(loop_fill)
+        dt, nbits = timed_loop(loop_ring)
+
+        # (c) the streaming API every N > 1 run uses for its e2e figure (sharded.ShardedBitStream), here on one GPU: the same
+        #     windows, chunks in flight instead of strictly alternating calls
+        sh.drain(collect)
+        bs = sharded.ShardedBitStream(sh, dem._stitch, 0, 1, None, None)
+
+        def run_stream(first, count):
+            for i in range(first, first + count):
+                bs.submit(windows[i % ring], sharded.SRC_HOST)
+            bs.drain()
+        run_stream(0, 8)
+        eng.shard_sync()
+        nb0 = sum(len(v[0]) for v in bs.bits.values())
+        t0 = time.perf_counter()
+        run_stream(8, n_e2e)
+        eng.shard_sync()
+        dt_stream = time.perf_counter() - t0
+        e2e_stream = {"value": step_samples * n_e2e / dt_stream / 1e6, "unit": "Msamples/s",
+                      "ms_per_step": dt_stream / e2e_steps * 1e3,
+                      "bits_per_step": (sum(len(v[0]) for v in bs.bits.values()) - nb0) / e2e_steps,
+                      "api": "sharded.ShardedBitStream on one GPU (the API of the N > 1 e2e figure): host samples -> stitched "
+                             "bits with chunks in flight, same page-locked windows"}
+        reg.close()
         e2e = {"value": step_samples * n_e2e / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * cps,
                "d2h_bytes_per_step": int(d2h) * cps, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "bits_per_step": nbits / e2e_steps,
-               "api": "demodulator.UHF.Demodulator.uploadAndFindCarrier + demodulate, strictly alternating (pinned chunk buffer)"}
+               "api": "demodulator.UHF.Demodulator.uploadAndFindCarrier(chunk) + demodulate(), strictly alternating; the chunks "
+                      "are overlapping windows of a page-locked sample ring (Demodulator.registerHostMemory), copied to the "
+                      "GPU from there inside the call",
+               "caller_fill_loop": {"value": step_samples * n_e2e / dt_fill / 1e6, "unit": "Msamples/s",
+                                    "ms_per_step": dt_fill / e2e_steps * 1e3, "bits_per_step": nbits_fill / e2e_steps,
+                                    "what": "the reference's caller unchanged (demodulator_process.py:287-337): every block is "
+                                            "first copied into the one pinned chunk buffer by the caller (8 N bytes of host "
+                                            "memcpy per chunk), then the same two calls"}}
     elif not args.no_e2e:
         # ONE ingest rank: rank 0 alone touches host samples (sigFIFO.py:147-181); H2D once, NVLink broadcast by the engine;
         # tail + D2H + bit post-processing on each chunk's owner, the chunk-to-chunk carry of checkSymbolOverlap passed from
@@ -613,18 +666,20 @@ def main():
                 return buf.numpy().tobytes()
             sh.drain(collect)
             bs = sharded.ShardedBitStream(sh, dem._stitch, rank, world, send, recv)
-            blocks = [stream[c * step_samples:(c + 1) * step_samples] for c in range(ring)] if rank == 0 else None
-            state = {"tail": np.zeros(ovl, np.complex64), "k": 0}
+            windows = reg = None
+            if rank == 0:        # the radio's samples: a page-locked ring; chunk c = its window [c * step, c * step + N)
+                ext = np.concatenate((np.zeros(ovl, np.complex64), stream))
+                reg = _native.host_register(ext)
+                windows = [ext[c * step_samples:c * step_samples + N] for c in range(ring)]
+            state = {"k": 0}
 
             def run(count):
                 for _ in range(count):
+                    src = None
                     if rank == 0:
-                        slot = bs.host_slot()
-                        slot[:ovl] = state["tail"]                 # overlap carry (demodulator_process.py:337)
-                        slot[ovl:] = blocks[state["k"] % ring]
-                        state["tail"] = slot[-ovl:].copy()
+                        src = windows[state["k"] % ring]
                         state["k"] += 1
-                    bs.submit(None, sharded.SRC_HOST)
+                    bs.submit(src, sharded.SRC_HOST)
                 bs.drain()                                         # in chunk order: the carries travel from chunk to chunk
             run(2 * world)
             eng.shard_sync()
@@ -637,6 +692,8 @@ def main():
             bs.finish()
             for w in sends:
                 w.wait()
+            if reg is not None:
+                reg.close()
             return dt, sum(len(v[0]) for v in bs.bits.values()) - nb0, n_e2e
 
         # a failure on any rank (or a carry that never arrives: the gloo group times out) must not take the device-resident
@@ -656,7 +713,7 @@ def main():
             e2e = {"value": step_samples * n_e2e / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * N * cps,
                    "d2h_bytes_per_step": int(88 + 4 * D * M + 12 * eng.max_sym + 2 * 8 * 157) * cps, "steps": e2e_steps,
                    "ms_per_step": dt / e2e_steps * 1e3, "bits_per_step": int(nb.item()) / e2e_steps,
-                   "api": "sharded.ShardedBitStream: host samples on rank 0 ONLY (pinned slot, one H2D per chunk), NVLink broadcast "
+                   "api": "sharded.ShardedBitStream: host samples on rank 0 ONLY (windows of a page-locked sample ring, one H2D per chunk), NVLink broadcast "
                           "of the chunk by the copy engines, bin-sharded search on all ranks, tail + D2H on the chunk's owner, bit "
                           "post-processing on the owner with the chunk-to-chunk carry passed owner to owner over gloo",
                    "note": "max over ranks of the wall time between barriers"}
@@ -751,7 +808,8 @@ def main():
         "value_with_h2d": {"value": value_h2d, "unit": "Msamples/s", "chunks": h2d_chunks,
                            "note": "same loop, every chunk copied from pinned host memory on the ingest rank inside the timed region"},
         "parity_vs_single_gpu": parity["ok"], "parity": parity,
-        "stage_ms": stages, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu, "verify": verify, "variants": variants,
+        "stage_ms": stages, "roofline": roof, "e2e": e2e, "e2e_stream": e2e_stream, "cpu_baseline": cpu, "verify": verify,
+        "variants": variants,
     }
     print(json.dumps(line))
     if dist is not None:

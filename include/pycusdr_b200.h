@@ -103,6 +103,17 @@ void* pcs_host_buffer(pcs_handle* h);
  * forward FFT.  Returns without synchronising. */
 int pcs_upload(pcs_handle* h);
 
+/* Chunks straight from the caller's own sample memory (extension of dem_base:1055-1060 / demodulator_process.py:287, where
+ * the caller copies every block into the one pinned buffer -- 8 * nfft bytes of host memcpy per chunk, more than the H2D
+ * copy costs).  pcs_host_register page-locks a range once (cudaHostRegister; e.g. the ring a receiver thread writes, of
+ * which consecutive chunks are overlapping windows: sigFIFO.py:147-181); pcs_set_host_source names complex64[nfft] inside
+ * such a range as the source of the NEXT pcs_upload / pcs_chunk_to_bits (one shot; NULL cancels).  The range must stay
+ * unchanged until the next synchronising call on the handle.  Pageable memory is refused (PCS_ERR_INVALID).
+ * pcs_upload_thresholded always uses the handle's own buffer (it clips in place). */
+int pcs_host_register(void* ptr, uint64_t bytes);
+int pcs_host_unregister(void* ptr);
+int pcs_set_host_source(pcs_handle* h, const void* chunk);
+
 /* Replaces __thresholdInput followed by uploadToGPU (STX backend: STX.py:13-20, dem_base:670-707, 548-558): the pinned
  * chunk is copied to HBM, clipped there in two passes to scale * mean(|x|) (scale = peakThresholdScale; the means are
  * float32 pairwise sums in np.mean's order), and copied back into the pinned buffer, which the reference clips in

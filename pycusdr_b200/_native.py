@@ -110,6 +110,9 @@ SYMBOLS = {
     "pcs_sync_search": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pcs_bit_xcorr": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, _P]),
     "pcs_topk_i32": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    "pcs_host_register": (C.c_int, [_P, C.c_uint64]),
+    "pcs_host_unregister": (C.c_int, [_P]),
+    "pcs_set_host_source": (C.c_int, [_P, _P]),
     "pcs_set_stream": (C.c_int, [_P, C.c_uint64]),
     "pcs_set_profiling": (C.c_int, [_P, C.c_int]),
     "pcs_get_profile": (C.c_int, [_P, _P, _P]),
@@ -181,6 +184,61 @@ def fill_gaps(idx, min_gap, nfft):
     if rc != 0:
         raise NativeError(rc, load().pcs_last_error().decode())
     return out[:min(n.value, len(out))].copy()
+
+
+class HostRegistration:
+    """A range of the caller's own host memory page-locked for direct H2D copies (``pcs_host_register``): typically the
+    sample ring a receiver writes into, of which consecutive chunks are overlapping windows (sigFIFO.py:147-181).  Keeps the
+    array alive; ``close()`` (or garbage collection) releases the page lock."""
+
+    def __init__(self, arr):
+        if not (isinstance(arr, np.ndarray) and arr.flags.c_contiguous and arr.nbytes > 0):
+            raise ValueError("host_register needs a non-empty C-contiguous NumPy array")
+        self.lib = load()
+        self.arr = arr
+        self.start = arr.__array_interface__["data"][0]
+        self.end = self.start + arr.nbytes
+        rc = self.lib.pcs_host_register(self.start, arr.nbytes)
+        if rc != 0:
+            raise NativeError(rc, self.lib.pcs_last_error().decode())
+        _registered.append(self)
+        _live.add(self)
+
+    def contains(self, ptr, nbytes):
+        return self.start <= ptr and ptr + nbytes <= self.end
+
+    def close(self):
+        if self.arr is not None:
+            if self in _registered:
+                _registered.remove(self)
+            self.lib.pcs_host_unregister(self.start)
+            self.arr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_registered = []
+
+
+def host_register(arr):
+    """Page-lock ``arr`` (in place, no copy) so that chunks that are views of it go to the GPU without a staging copy."""
+    return HostRegistration(arr)
+
+
+def registered_ptr(a, nbytes):
+    """Address of ``a``'s buffer when ``a`` is a C-contiguous array of exactly ``nbytes`` bytes inside a registered range,
+    else None."""
+    if not isinstance(a, np.ndarray) or not _registered or a.nbytes != nbytes or not a.flags.c_contiguous:
+        return None
+    ptr = a.__array_interface__["data"][0]
+    for r in _registered:
+        if r.contains(ptr, nbytes):
+            return ptr
+    return None
 
 
 def _ptr(a):
@@ -461,6 +519,10 @@ class Engine:
         self._check(self.lib.pcs_upload_thresholded(self._h, float(scale), _ptr(self._clip_idx), self.nfft, C.byref(n),
                                                     _ptr(self._clip_thr)))
         return self._clip_idx[:n.value].copy(), self._clip_thr.copy()
+
+    def set_host_source(self, ptr):
+        """The next ``upload`` / ``chunk_to_bits`` copies complex64[nfft] from this page-locked address (one shot)."""
+        self._check(self.lib.pcs_set_host_source(self._h, _P(ptr)))
 
     def upload_device(self, dev_ptr):
         self._check(self.lib.pcs_upload_device(self._h, _P(dev_ptr)))

@@ -93,6 +93,7 @@ struct pcs_handle {
     size_t rb_off[7] = {}, rb_bytes = 0;
     // pinned host memory
     float2 *h_x = nullptr, *h_sigwin = nullptr, *h_noisewin = nullptr;
+    const float2* h_src = nullptr;     // one-shot: the next pcs_upload copies from this page-locked caller buffer instead of h_x
     DevResult* h_res = nullptr;
     float *h_E = nullptr, *h_mag = nullptr;
     int *h_sym = nullptr, *h_centre = nullptr;
@@ -819,6 +820,39 @@ int pcs_create(const pcs_config* cfg, const int32_t* shifts, const float* masks,
 }
 
 void* pcs_host_buffer(pcs_handle* h) { return h ? (void*)h->h_x : nullptr; }
+
+// Page-lock / release a range of the caller's own memory (e.g. the sample ring a receiver thread writes into) so that chunks
+// can be copied to HBM straight from it: the caller's fill of the handle's pinned buffer (demodulator_process.py:287) is
+// 8 * nfft bytes of host memcpy per chunk, more than the H2D copy itself costs.
+int pcs_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return fail(PCS_ERR_INVALID, "null or empty range");
+    CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return PCS_OK;
+}
+
+int pcs_host_unregister(void* ptr) {
+    if (!ptr) return fail(PCS_ERR_INVALID, "null pointer");
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return PCS_OK;
+}
+
+int pcs_set_host_source(pcs_handle* h, const void* chunk) {
+    if (!h) return fail(PCS_ERR_INVALID, "null handle");
+    if (!chunk) { h->h_src = nullptr; return PCS_OK; }
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // both ends of the chunk must be page-locked: a pageable source would make the "asynchronous" copy a staged, blocking one
+    const char* ends[2] = {reinterpret_cast<const char*>(chunk), reinterpret_cast<const char*>(chunk) + sizeof(float2) * (size_t)h->N - 1};
+    for (const char* e : ends) {
+        cudaPointerAttributes at{};
+        const cudaError_t rc = cudaPointerGetAttributes(&at, e);
+        if (rc != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return fail(PCS_ERR_INVALID, "pcs_set_host_source: the chunk is not in page-locked host memory (pcs_host_register it)");
+        }
+    }
+    h->h_src = reinterpret_cast<const float2*>(chunk);
+    return PCS_OK;
+}
 int32_t pcs_max_symbols(const pcs_handle* h) { return h ? h->max_sym : 0; }
 int64_t pcs_launch_count(const pcs_handle* h) { return h ? h->launches : 0; }
 uint64_t pcs_stream(const pcs_handle* h) { return h ? (uint64_t)(uintptr_t)h->stream : 0; }
@@ -1266,7 +1300,9 @@ static int enqueue_chunk(pcs_handle* h) {
 int pcs_upload(pcs_handle* h) {
     if (!h) return fail(PCS_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
+    const float2* from = h->h_src ? h->h_src : h->h_x;
+    h->h_src = nullptr;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x, from, sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
     h->d_x_cur = h->d_x_base = h->d_x;
     h->uploaded = true;
     h->searched = h->demodulated = false;
@@ -1290,6 +1326,7 @@ int pcs_upload_thresholded(pcs_handle* h, float scale, int64_t* clipped_idx, int
         if (int rc = dev_alloc(h, &h->d_thr_bits, (size_t)N / 32)) return rc;
         CUDA_TRY(cudaHostAlloc((void**)&h->h_thr_bits, sizeof(unsigned int) * (N / 32) + 2 * sizeof(float), cudaHostAllocDefault));
     }
+    h->h_src = nullptr;       // clipping is in place in the handle's own buffer: a pending caller source does not apply
     float* mag = h->d_p;      // free until the demod stage of this chunk writes it
     CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(float2) * N, cudaMemcpyHostToDevice, h->stream));
     threshold_abs_kernel<<<nb, 128, 0, h->stream>>>(h->d_x, mag, h->d_thr_partial);

@@ -8,7 +8,7 @@ class Demodulator(Demodulator_base):
     def uploadAndFindCarrier(self, samples):
         if self.fused and self.one_call and self._stitch is not None:
             return self.chunkToBits(samples)      # same results, one native call for the whole chunk
-        self.uploadToGPU(samples)
+        self.uploadToGPU(samples, direct=True)      # (no input thresholding on this backend: the samples are only read)
         return self.findUHF(samples)
 
     def demodulate(self):

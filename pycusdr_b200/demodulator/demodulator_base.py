@@ -165,17 +165,33 @@ class Demodulator:
         """Pinned complex64[Nfft] the caller fills in place (dem_base:1055-1060)."""
         return self.GPU_bufSignalTime_cpu_handle
 
-    def _as_chunk_buffer(self, samples):
+    def _as_chunk_buffer(self, samples, direct=False):
         """The reference transforms the pinned buffer whatever ``samples`` is (dem_base:557); a caller
-        that passes another array gets it copied in, which is what it meant."""
+        that passes another array gets it copied in, which is what it meant.  ``direct``: a complex64[Nfft] view of memory
+        the caller page-locked with ``registerHostMemory`` is NOT copied -- the next upload reads it in place."""
         buf = self.GPU_bufSignalTime_cpu_handle
-        if samples is not buf and not (isinstance(samples, np.ndarray) and np.shares_memory(samples, buf)):
+        if samples is buf:
+            return buf
+        if direct:
+            ptr = _native.registered_ptr(samples, 8 * self.Nfft) if getattr(samples, "dtype", None) == np.complex64 else None
+            if ptr is not None:
+                self._engine.set_host_source(ptr)
+                return samples
+        if not (isinstance(samples, np.ndarray) and np.shares_memory(samples, buf)):
             buf[:] = samples
         return buf
 
+    @staticmethod
+    def registerHostMemory(arr):
+        """Extension: page-lock the caller's own sample memory (e.g. the ring a receiver thread fills; consecutive chunks are
+        overlapping windows of it).  ``uploadAndFindCarrier(view)`` with a complex64[Nfft] view of it then copies to the GPU
+        straight from there: the fill of the pinned chunk buffer (demodulator_process.py:287, 8 * Nfft bytes of host memcpy
+        per chunk) and the overlap carry (:337) disappear.  Returns the registration (``close()`` releases the page lock)."""
+        return _native.host_register(arr)
+
     # -- a4 --------------------------------------------------------------------------------------
-    def uploadToGPU(self, samples):
-        self._as_chunk_buffer(samples)
+    def uploadToGPU(self, samples, direct=False):
+        self._as_chunk_buffer(samples, direct)
         self._engine.upload()
         self._pending = None
         self._bits_ready = None
@@ -207,7 +223,7 @@ class Demodulator:
         """uploadToGPU + findUHF + the whole of demodulate() in ONE native call (``pcs_chunk_to_bits``): the fused
         schedule with the symbol tables handed to the stitcher inside the library.  Returns what findUHF returns; the
         bits are parked for the demodulate() call that follows (dem_base:548-632, 765-859)."""
-        self._as_chunk_buffer(samples)
+        self._as_chunk_buffer(samples, direct=True)
         (res, E, sym, centre, mag, means, bits, centres8, trust8, err) = self._engine.chunk_to_bits(
             self._stitch, self.doppCyperSymNorm, self.clippedPeakIPure)
         self._pending = None

@@ -514,3 +514,52 @@ def test_streaming_ingest_equals_the_chunk_loop(inflight, blk):
         np.testing.assert_equal(g["doppler"], r["doppler"])
         np.testing.assert_equal(g["SNR"], r["SNR"])
         assert g["spSymEst"] == r["spSymEst"]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_chunks_from_a_registered_sample_ring_equal_the_fill_loop(fused):
+    """Extension of the class contract (Demodulator.registerHostMemory, pcs_host_register / pcs_set_host_source): chunks
+    passed as overlapping windows of a page-locked sample ring go to the GPU from there, without the caller's fill of the one
+    pinned chunk buffer (demodulator_process.py:287) -- every output must equal what the unchanged caller loop produces."""
+    from pycusdr_b200 import sharded
+    from pycusdr_b200.demodulator import UHF
+    conf = load_conf("benchmark/bench_GMSK.json")
+    P = protocol_for(conf)
+    sig, _ = S.bench_stream("GMSK", 11, seed=19)
+    ref = O.run_stream(UHF.Demodulator(conf, P, RADIO, fused=fused), sig)
+    dem = UHF.Demodulator(conf, P, RADIO, fused=fused)
+    N, ovl = dem.Nfft, dem.sigOverlap
+    step = N - ovl
+    ring = np.concatenate((np.zeros(ovl, np.complex64), np.ascontiguousarray(sig, dtype=np.complex64)))
+    before = ring.copy()
+    reg = dem.registerHostMemory(ring)
+    own = dem.get_signalBufferHostPointer()
+    own[:] = np.complex64(7 + 7j)             # must not be what gets transformed
+    assert len(ref) > 5
+    for c, r in enumerate(ref):
+        freq, sdev, clipped, snr = dem.uploadAndFindCarrier(ring[c * step:c * step + N])
+        bits, centres, trust, sp = dem.demodulate()
+        np.testing.assert_array_equal(bits, r["data"])
+        np.testing.assert_array_equal(trust, r["trust"])
+        np.testing.assert_equal(freq, r["doppler"])
+        np.testing.assert_equal(snr, r["SNR"])
+        assert sp == r["spSymEst"]
+    np.testing.assert_array_equal(ring, before)            # read in place, never written
+    assert np.all(own == np.complex64(7 + 7j))
+    # the streaming engine takes the same windows (PCS_SRC_HOST with a caller pointer): identical bit stream
+    dem2 = UHF.Demodulator(conf, P, RADIO)
+    sh = sharded.ShardedStream(dem2._engine, 0, 1, lambda o: [o], lag=2)
+    bs = sharded.ShardedBitStream(sh, dem2._stitch, 0, 1, None, None)
+    for c in range(len(ref)):
+        bs.submit(ring[c * step:c * step + N], sharded.SRC_HOST)
+    bs.finish()
+    for c, r in enumerate(ref):
+        np.testing.assert_array_equal(bs.bits[c][0], r["data"])
+        np.testing.assert_array_equal(bs.bits[c][2], r["trust"])
+    reg.close()
+    # a window of memory that is not page-locked takes the copy path (and still gives the same answer) ...
+    dem.uploadAndFindCarrier(ring[0:N].copy())
+    # ... and the native call refuses a pageable source instead of silently staging it
+    from pycusdr_b200 import _native
+    with pytest.raises(_native.NativeError):
+        dem._engine.set_host_source(before.__array_interface__["data"][0])

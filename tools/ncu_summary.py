@@ -63,7 +63,19 @@ def main():
         f.write("\n".join(lines + extra) + "\n")
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     t = json.load(open(tpath))
-    t[short] = {"dram_bytes_per_launch": int(dram), "capture": tag, "workload": workload, "n_gpus": 1}
+    def num(metric):
+        return float(rr[rcol[metric]].replace(",", "")) if metric in rcol else None
+    dur = num("gpu__time_duration.sum")
+    if dur is not None:
+        dur *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[rcol["gpu__time_duration.sum"]], 1.0)
+    t[short] = {"dram_bytes_per_launch": int(dram), "capture": tag, "workload": workload, "n_gpus": 1,
+                # what bench.py turns into roofline.executed_fma_pipe_frac (FMA-pipe busy cycles of the capture, rescaled to the
+                # live kernel time) -- measured, not hand-counted
+                "duration_us": dur,
+                "pipe_fma_cycles_active_pct": num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                "inst_executed_pipe_fma_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "lsu_wavefronts_pct_of_peak": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                "registers_per_thread": num("launch__registers_per_thread")}
     json.dump(t, open(tpath, "w"), indent=2)
     print(short, "dram bytes per launch", int(dram))
 
