@@ -287,6 +287,9 @@ def run_c5(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_ch, ring = 64, 8
     mine = [c for c in range(n_ch) if c % world == rank]
+    # chunks in flight per GPU: a C3-sized chunk is ~ 0.2 ms of dependent small kernels, so a rank with few channels keeps
+    # more steps of each channel in flight (64 chunks per GPU whatever the world size)
+    depth = max(2, min(8, n_ch // max(len(mine), 1)))
     dems, ptrs, keep = [], [], []
     step_samples = 0
     for c in mine:
@@ -298,30 +301,35 @@ def run_c5(args):
         dev = torch.from_numpy(W.chunks_from_stream(stream, N, ovl, ring)).cuda()
         keep.append(dev)
         ptrs.append([dev[i].data_ptr() for i in range(ring)])
-        dems.append([UHF.Demodulator(conf, protocol_for(conf), RADIO) for _ in range(2)])
-    engs = [[d._engine for d in pair] for pair in dems]          # two handles per channel: step i on handle i % 2
+        dems.append([UHF.Demodulator(conf, protocol_for(conf), RADIO) for _ in range(depth)])
+    engs = [[d._engine for d in pair] for pair in dems]          # ``depth`` handles per channel: step i on handle i % depth
     streams = [torch.cuda.ExternalStream(e.stream) for pair in engs for e in pair]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def enqueue(i):
         for pair, p in zip(engs, ptrs):
-            pair[i % 2].enqueue_device(p[i % ring])
+            pair[i % depth].enqueue_device(p[i % ring])
 
     def collect(i):
         acc = 0
         for pair in engs:
-            acc += int(pair[i % 2].fetch()[0].shift)
+            acc += int(pair[i % depth].fetch()[0].shift)
         return acc
 
     def run(first, count):
-        """one chunk of every channel per step; the results of step i - 1 are collected after step i is enqueued"""
+        """one chunk of every channel per step; the results of step i - (depth - 1) are collected after step i is enqueued"""
         acc = 0
+        done = first
         for i in range(first, first + count):
             enqueue(i)
-            if i > first:
-                acc += collect(i - 1)
-        return acc + collect(first + count - 1)
-    warm = max(args.warmup, 4)
+            if i - done >= depth - 1:
+                acc += collect(done)
+                done += 1
+        while done < first + count:
+            acc += collect(done)
+            done += 1
+        return acc
+    warm = max(args.warmup, 4, depth)
     run(0, warm)
     torch.cuda.synchronize()
     if dist is not None:
@@ -356,7 +364,7 @@ def run_c5(args):
                                    "per step", "channels": n_ch, "channels_per_gpu": len(mine), "samples_per_step": n_ch * step_samples,
                        "x_real_time_per_channel": value * 1e6 / n_ch / 153600.0,
                        "l2": f"{ring} distinct chunks per channel", "parallelism": "channels sharded over GPUs, no exchange"},
-            "clocks": clocks, "gpu_launches": int(launches), "launch_mode": "cuda_graph per channel, two handles per channel (steps pipelined)",
+            "clocks": clocks, "gpu_launches": int(launches), "launch_mode": f"cuda_graph per channel, {depth} handles per channel (steps pipelined)",
             "checksum": checksum}))
     if dist is not None:
         dist.destroy_process_group()
