@@ -398,7 +398,8 @@ def main():
     ap.add_argument("--items-per-cta", type=int, default=0, help="tuning knob of the shifted-filter search kernel")
     ap.add_argument("--warps20", action="store_true", help="tuning knob: 96-register build of the shifted-filter kernel")
     ap.add_argument("--ring", type=int, default=0, help="chunk ring depth of the sharded engine (0 = choose)")
-    ap.add_argument("--lag", type=int, default=2, help="owned chunks kept in flight before the oldest is collected (0..3)")
+    ap.add_argument("--lag", type=int, default=-1, help="owned chunks kept in flight before the oldest is collected (0..7); "
+                    "default 2 on several GPUs (= 2 * world chunks), 6 on one")
     ap.add_argument("--watchdog-s", type=int, default=600, help="abort the process after this many seconds")
     ap.add_argument("--doppler-bins", type=int, default=0,
                     help="experiment: override doppCarrierSteps (e.g. one rank's slice of the bins on a single GPU); the "
@@ -470,6 +471,8 @@ def main():
     D, M = eng.D, eng.M
     plan = eng.plan()
     S_nom = N // cr["samplesPerSym"]
+    if args.lag < 0:
+        args.lag = 2 if world > 1 else 6
     sh = sharded.ShardedStream(eng, rank, world, all_gather, ring=args.ring, lag=args.lag)
     info = eng.shard_info()
     lo, hi = sh.slices[rank]
@@ -748,6 +751,9 @@ def main():
     search_ms = s_ms / max(s_cnt, 1)
     kname = ("search_fs256_kernel" if (args.search_form == 0 and M <= 16) else "search_os256_kernel") \
         if plan["log2_block"] == 8 else "search_os_kernel"
+    bank = eng.bank_factor()
+    if bank[0]:             # long filters that are combinations of a few basis segments (bank_factor.cu): R transforms per item
+        kname = "search_fb_kernel"
     roof = {
         "bound": "fp32", "kernel": kname,
         "achieved": k_flop / (search_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -805,6 +811,7 @@ def main():
         "details": {"x_real_time": value * 1e6 / fs, "ms_per_chunk": ms_step / cps,
                     "path": {1: "overlap_save", 2: "full", 3: "parseval"}.get(plan["path"]),
                     "block": 2 ** plan["log2_block"], "valid_per_block": plan["valid_per_block"],
+                    "bank_factor": ({"segment_taps": bank[1], "segments": bank[2], "basis_filters": bank[3]} if bank[0] else None),
                     "l2": f"ring of {ring} distinct chunks = {ring_bytes >> 20} MiB (> 126 MiB L2) in rank 0's HBM, one per chunk",
                     "engine": {"ring": info["ring"], "lanes": info["lanes"], "result_stages": info["stages"], "lag": args.lag},
                     "parallelism": "single GPU, streaming engine (two search lanes + tail stream)" if world == 1 else (

@@ -62,7 +62,8 @@ typedef struct {
                                         CUDA graph, bit 1: 96-register build of the shifted-filter kernel (20 warps per SM); [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
                                         8+: (bin, block) items per CTA of the shifted-filter search kernel (0 = 64); [2] form of the
                                         256-point search: 0 = shifted filters (block spectra shared by all bins), 1 / 2 = rotate the
-                                        chunk per bin with the block spectrum in shared memory / registers (comparison variants) */
+                                        chunk per bin with the block spectrum in shared memory / registers (comparison variants), 3 = shifted
+                                        filters with the long-filter bank never factorised (pcs_factorise_bank; comparison variant) */
 } pcs_config;
 
 /* Per-chunk scalar results (filled by pcs_search / pcs_demod / pcs_process). */
@@ -189,6 +190,28 @@ typedef struct {
     int64_t device_bytes;   /* HBM allocated by the handle */
 } pcs_plan_info;
 int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info);
+
+/* Segment factorisation of the matched-filter bank (plan-time helper of pcs_create for filters too long for the 256-point
+ * kernel; host only, no GPU -- exported so that the tables can be checked without one).  The reference's FSK-2 bank
+ * (pyCuSDR/protocol/FSK2_base.py:17-46: 2^k templates, each k one-symbol tone segments with a continuous phase; CC11xx:
+ * 8 x 3 x 128 taps) has only R = 2 distinct segments up to a complex constant.  With the taps g_m[n] = IFFT(Mk[m]) on
+ * n = -support_neg .. support_pos cut into J segments of S taps counted from the support_pos end,
+ *     g_m[n] = sum_j c[m][j] * b_{sel[m][j]}[n + j S],     b_r supported on n = support_pos - S + 1 .. support_pos,
+ * every filter output is y_m[i] = sum_j c[m][j] * u_{sel[m][j]}[i + j S] with u_r = b_r * x, so the search needs R inverse
+ * transforms per (bin, block) instead of M (a6-a8, kern:339-373, 421-480: same numbers to fp32 rounding).  The structure is
+ * detected from `masks` (the spectra given to pcs_create), never assumed; *num_basis = 0 means none was found, or it would
+ * not pay, or it failed the acceptance test (the factorised bank must reproduce Mk[m][(k N/B - shift) % N] to 1e-5 of
+ * the peak).  Outputs, sized by the caller for the maxima: sel_out int32[M * PCS_FB_MAX_SEG] (used [M][J]), coef_out
+ * complex64[D * M * PCS_FB_MAX_SEG] (used [D][M][J]; includes the bin's exp(-2 pi i shift j S / N)), basis_spec_out
+ * complex64[D * PCS_FB_MAX_BASIS * B] (used [D][R][B], B = 2**log2_block: the B-point spectra of the bin's shifted basis
+ * filters, scaled like the kernel's filter spectra); each may be NULL. */
+#define PCS_FB_MAX_SEG 4
+#define PCS_FB_MAX_BASIS 4
+int pcs_factorise_bank(const float* masks /* complex64[M*nfft] */, int32_t nfft, int32_t num_masks, int32_t support_pos,
+                       int32_t support_neg, const int32_t* shifts, int32_t num_shifts, int32_t log2_block, int32_t* seg_len,
+                       int32_t* num_seg, int32_t* num_basis, int32_t* sel_out, float* coef_out, float* basis_spec_out);
+/* What the handle's search uses: out[0] = 1 when the factorised bank is active, out[1..3] = S, J, R. */
+int pcs_get_bank_factor(const pcs_handle* h, int32_t out[4]);
 
 /* Kernel launch counter (all launches issued through this handle since creation). */
 int64_t pcs_launch_count(const pcs_handle* h);

@@ -74,6 +74,9 @@ SYMBOLS = {
     "pcs_get_demod_surface": (C.c_int, [_P, C.c_int32, _P]),
     "pcs_get_demod_magnitudes": (C.c_int, [_P, _P, _P]),
     "pcs_get_plan": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "pcs_factorise_bank": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P]),
+    "pcs_get_bank_factor": (C.c_int, [_P, _P]),
     "pcs_launch_count": (C.c_int64, [_P]),
     "pcs_stream": (C.c_uint64, [_P]),
     "pcs_set_bin_range": (C.c_int, [_P, C.c_int32, C.c_int32]),
@@ -173,6 +176,35 @@ def mean_abs_c64(z):
     if rc != 0:
         raise NativeError(rc, load().pcs_last_error().decode())
     return np.float32(out.value)
+
+
+FB_MAX_SEG, FB_MAX_BASIS = 4, 4
+
+
+def factorise_bank(masks, support_pos, support_neg, shifts, log2_block):
+    """Segment factorisation of a filter bank (``pcs_factorise_bank``; host only, no GPU).
+
+    ``masks``: complex64[M, nfft] spectra as given to ``pcs_create``.  Returns ``None`` when the bank does not factorise
+    (or it would not pay), else a dict with ``S`` (segment length), ``J`` (segments per filter), ``R`` (basis filters),
+    ``sel`` int32[M, J], ``coef`` complex64[D, M, J] and ``basis_spec`` complex64[D, R, 2**log2_block].
+    """
+    masks = np.ascontiguousarray(masks, dtype=np.complex64)
+    shifts = np.ascontiguousarray(shifts, dtype=np.int32)
+    M, N = masks.shape
+    D, B = len(shifts), 1 << int(log2_block)
+    sel = np.zeros(M * FB_MAX_SEG, dtype=np.int32)
+    coef = np.zeros(D * M * FB_MAX_SEG, dtype=np.complex64)
+    spec = np.zeros(D * FB_MAX_BASIS * B, dtype=np.complex64)
+    S, J, R = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    rc = load().pcs_factorise_bank(_ptr(masks), N, M, int(support_pos), int(support_neg), _ptr(shifts), D, int(log2_block),
+                                   C.byref(S), C.byref(J), C.byref(R), _ptr(sel), _ptr(coef), _ptr(spec))
+    if rc != 0:
+        raise NativeError(rc, load().pcs_last_error().decode())
+    if R.value == 0:
+        return None
+    S, J, R = S.value, J.value, R.value
+    return {"S": S, "J": J, "R": R, "sel": sel[:M * J].reshape(M, J).copy(),
+            "coef": coef[:D * M * J].reshape(D, M, J).copy(), "basis_spec": spec[:D * R * B].reshape(D, R, B).copy()}
 
 
 def fill_gaps(idx, min_gap, nfft):
@@ -631,6 +663,12 @@ class Engine:
         return {n: getattr(info, n) for n, _ in PlanInfo._fields_}
 
     # -- bin sharding ----------------------------------------------------------------------------
+    def bank_factor(self):
+        """(active, S, J, R) of the factorised filter bank the generic search uses (``pcs_get_bank_factor``)."""
+        out = np.zeros(4, dtype=np.int32)
+        self._check(load().pcs_get_bank_factor(self._h, _ptr(out)))
+        return tuple(int(v) for v in out)
+
     def set_bin_range(self, lo, hi):
         self._check(self.lib.pcs_set_bin_range(self._h, int(lo), int(hi)))
 

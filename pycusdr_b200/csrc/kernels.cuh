@@ -240,6 +240,124 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a6 + a7 + a8 for a FACTORISED filter bank (bank_factor.cu; the reference's FSK-2 bank, CC11xx: M = 8 filters of 3 x 128
+// taps are combinations of R = 2 one-symbol basis filters).  One group per (bin, block) item:
+//   1. the item's block spectrum (block_spectra_kernel's table) goes to shared memory,
+//   2. R inverse transforms of (block spectrum x the bin's basis spectrum r) leave u_r = b_r * x in shared memory in natural
+//      order (u_0 .. u_{R-2} in their own buffers, the last one over the block spectrum, which is dead by then),
+//   3. y_m[i] = sum_j c[d][m][j] u_{sel[m][j]}[i + j S] for the block's valid outputs, two adjacent outputs per thread and
+//      step (one 128-bit shared-memory load per term), sum and max of |y|^2 per mask as in search_os_kernel.
+// R transforms instead of M per item; the combination costs J 128-bit loads + 2 J packed FMAs per output pair and mask.
+// The offset of the maximum is recovered by search_os_kernel<.., LOCATE = true> with the unfactorised spectra.
+// ---------------------------------------------------------------------------------------------
+struct FbSearchParams {
+    const float2* __restrict__ xbs;     // [nblk][B] block spectra of the unrotated chunk
+    const float2* __restrict__ gbasis;  // [D][R][B] per-bin basis spectra
+    const float2* __restrict__ coef;    // [D][M][J]
+    const int* __restrict__ sel;        // [M][J] basis index of every segment
+    const float2* __restrict__ tw;      // [B] exp(-2 pi i t / B)
+    float* __restrict__ psum;           // [D][M][nblk]
+    float* __restrict__ pmax;           // [D][M][nblk]
+    int N, D, M, nblk, V, Lpos, R, S;
+};
+
+PCS_DEVINL float2 cfma(float2 c, float2 a, float2 y) {      // y + c a: two FFMA2
+    const float2 t = __ffma2_rn(make_float2(c.x, c.x), a, y);
+    return __ffma2_rn(make_float2(c.y, c.y), make_float2(-a.y, a.x), t);
+}
+
+template <int LOGB, int G, int J>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T <= 128) ? 3 : 1) search_fb_kernel(FbSearchParams p) {
+    using S = FftShape<LOGB>;
+    constexpr int B = S::B, T = S::T, NW = (T + 31) / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* smem = reinterpret_cast<float2*>(smem_raw);
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const size_t gstride = (size_t)3 * S::WORK + (size_t)(p.R - 1) * B;
+    float2* work0 = smem + (size_t)g * gstride;
+    float2* work1 = work0 + S::WORK;
+    float2* xb = work1 + S::WORK;       // the item's block spectrum (padded layout), later u_{R-1} (natural, unpadded)
+    float2* ub = xb + S::WORK;          // u_0 .. u_{R-2}, B each
+    float* red = reinterpret_cast<float*>(smem + (size_t)G * gstride) + (size_t)g * p.M * NW * 2;
+    const int bar_id = 1 + g;
+
+    const long long item = (long long)blockIdx.x * G + g;
+    if (item >= (long long)p.nblk * p.D) return;      // whole group leaves (own barrier id)
+    const int blk = (int)(item % p.nblk), d = (int)(item / p.nblk);
+    const int n0 = blk * p.V;
+    {
+        const float2* __restrict__ xs = p.xbs + (size_t)blk * B;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xb[padi(t + r * T)] = __ldg(&xs[t + r * T]);
+    }
+    group_sync<T>(bar_id);
+    for (int r = 0; r < p.R; ++r) {
+        const float2* __restrict__ gm = p.gbasis + ((size_t)d * p.R + r) * B;
+        float2* __restrict__ dst = r == p.R - 1 ? xb : ub + (size_t)r * B;
+        auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
+        auto sink = [&](int i, float2 v, int) { dst[i] = v; };
+        group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
+    }
+    group_sync<T>(bar_id);
+
+    const int lo = p.Lpos, hi = p.Lpos + min(p.V, p.N - n0);     // valid outputs of the block: lo <= i < hi
+    const int lane = t & 31, warp = t >> 5;
+    for (int m = 0; m < p.M; ++m) {
+        float2 c[J];
+        const float2* up[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            c[j] = __ldg(&p.coef[((size_t)d * p.M + m) * J + j]);
+            const int r = __ldg(&p.sel[m * J + j]);
+            up[j] = (r == p.R - 1 ? xb : ub + (size_t)r * B) + j * p.S;
+        }
+        float sum = 0.f, best = 0.f;
+#pragma unroll
+        for (int q = 0; q < B / (2 * T); ++q) {
+            const int i0 = 2 * (t + T * q);
+            if (i0 < hi) {
+                float4 a = *reinterpret_cast<const float4*>(up[0] + i0);
+                float2 y0 = cmul(c[0], make_float2(a.x, a.y)), y1 = cmul(c[0], make_float2(a.z, a.w));
+#pragma unroll
+                for (int j = 1; j < J; ++j) {
+                    a = *reinterpret_cast<const float4*>(up[j] + i0);
+                    y0 = cfma(c[j], make_float2(a.x, a.y), y0);
+                    y1 = cfma(c[j], make_float2(a.z, a.w), y1);
+                }
+                const float m0 = i0 >= lo ? cabs2(y0) : 0.f;
+                const float m1 = (i0 + 1 >= lo && i0 + 1 < hi) ? cabs2(y1) : 0.f;
+                sum += m0;
+                sum += m1;
+                best = fmaxf(best, fmaxf(m0, m1));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (lane == 0) {
+            float* r = red + ((size_t)m * NW + warp) * 2;
+            r[0] = sum;
+            r[1] = best;
+        }
+    }
+    group_sync<T>(bar_id);
+    for (int m = t; m < p.M; m += T) {
+        float sum = 0.f, best = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float* r = red + ((size_t)m * NW + w) * 2;
+            sum += r[0];
+            best = fmaxf(best, r[1]);
+        }
+        const size_t o = ((size_t)d * p.M + m) * p.nblk + blk;
+        p.psum[o] = sum;
+        p.pmax[o] = best;
+    }
+}
+
 // Block spectra of the unrotated chunk for the shifted-filter form of the generic kernel: one group per block.
 template <int LOGB, int G>
 __global__ void __launch_bounds__(G * FftShape<LOGB>::T) block_spectra_kernel(const float2* __restrict__ x,

@@ -118,6 +118,11 @@ struct pcs_handle {
     int cur_lane = 0;
     const float4* xbs_ext = nullptr;   // when set, the next shifted-filter search reads these block spectra instead of computing them
     float2* d_gs_os = nullptr;         // per-bin filter spectra of the generic kernel's shifted-filter form (natural order)
+    // factorised filter bank (bank_factor.cu): R basis filters, J segments of S taps per filter; search_fb_kernel
+    bool fb = false;
+    int fb_S = 0, fb_J = 0, fb_R = 0;
+    float2 *d_fb_basis = nullptr, *d_fb_coef = nullptr;   // [D][R][B], [D][M][J]
+    int* d_fb_sel = nullptr;                               // [M][J]
     int fs_items = 0;                  // items (bin, block) per CTA; 0 = choose per launch
     int fs_items_cap = 0;              // upper bound for the chosen value (0 = none)
     float *d_psum256 = nullptr, *d_pmax256 = nullptr, *d_part_sum = nullptr, *d_part_max = nullptr;   // rotate-form kernels
@@ -377,6 +382,67 @@ static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p, bool locat
     return 0;
 }
 
+// Factorised bank: block spectra (as for the shifted-filter form), then search_fb_kernel with G = max(1, 2048 / B) groups
+// per CTA (three 128-thread CTAs per SM up to B = 2048).
+template <int LOGB, int GBS, int G, int J>
+static int launch_search_fb_tj(pcs_handle* h, const OsSearchParams& p) {
+    using S = FftShape<LOGB>;
+    constexpr int NW = (S::T + 31) / 32;
+    const size_t bs_smem = (size_t)GBS * 2 * S::WORK * sizeof(float2);
+    auto bs = block_spectra_kernel<LOGB, GBS>;
+    static size_t bs_configured[PCS_MAX_DEVICES] = {};
+    if (bs_configured[h->cfg.device] < bs_smem) {
+        CUDA_TRY(cudaFuncSetAttribute(bs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
+        bs_configured[h->cfg.device] = bs_smem;
+    }
+    bs<<<(p.nblk + GBS - 1) / GBS, GBS * S::T, bs_smem, h->stream>>>(p.x, p.tw, h->osb[h->cur_lane].xbs, p.N, p.nblk, p.V, p.Lpos);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    FbSearchParams q{};
+    q.xbs = p.xbs; q.tw = p.tw; q.psum = p.psum; q.pmax = p.pmax;
+    q.gbasis = h->d_fb_basis + (((size_t)h->bin_lo * h->fb_R) << LOGB);
+    q.coef = h->d_fb_coef + (size_t)h->bin_lo * h->M * J;
+    q.sel = h->d_fb_sel;
+    q.N = p.N; q.D = p.D; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos; q.R = h->fb_R; q.S = h->fb_S;
+    const size_t smem = (size_t)G * ((size_t)3 * S::WORK + (size_t)(q.R - 1) * S::B) * sizeof(float2) +
+                        (size_t)G * p.M * NW * 2 * sizeof(float);
+    auto kern = search_fb_kernel<LOGB, G, J>;
+    static size_t configured[PCS_MAX_DEVICES] = {};
+    if (configured[h->cfg.device] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[h->cfg.device] = smem;
+    }
+    const long long items = (long long)p.nblk * p.D;
+    const int grid = (int)((items + G - 1) / G);
+    h->search_ctas = grid;
+    h->search_smem = (int)smem;
+    kern<<<grid, G * S::T, smem, h->stream>>>(q);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int LOGB, int GBS, int G>
+static int launch_search_fb_t(pcs_handle* h, const OsSearchParams& p) {
+    switch (h->fb_J) {
+        case 2: return launch_search_fb_tj<LOGB, GBS, G, 2>(h, p);
+        case 3: return launch_search_fb_tj<LOGB, GBS, G, 3>(h, p);
+        case 4: return launch_search_fb_tj<LOGB, GBS, G, 4>(h, p);
+    }
+    return fail(PCS_ERR_INVALID, "factorised bank with %d segments", h->fb_J);
+}
+static size_t fb_smem_bytes(int logB, int R, int M) {
+    const size_t B = (size_t)1 << logB, work = B + (B >> 4), T = B / 16, G = std::max<size_t>(1, 2048 / B), NW = (T + 31) / 32;
+    return G * (3 * work + (size_t)(R - 1) * B) * sizeof(float2) + G * M * NW * 2 * sizeof(float);
+}
+static int launch_search_fb(pcs_handle* h, const OsSearchParams& p) {
+    switch (h->logB) {
+        case 10: return launch_search_fb_t<10, 4, 2>(h, p);
+        case 11: return launch_search_fb_t<11, 2, 1>(h, p);
+        case 12: return launch_search_fb_t<12, 1, 1>(h, p);
+    }
+    return fail(PCS_ERR_INVALID, "factorised bank with 2^%d-point blocks", h->logB);
+}
+
 template <int LOGB, int G>
 static int launch_demod_os_t(pcs_handle* h, const OsDemodParams& p) {
     using S = FftShape<LOGB>;
@@ -493,7 +559,8 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
     const int L256 = 256 - L + 1;
     const bool fast256_will_run = (h->cfg.log2_block == 0 || h->cfg.log2_block == 8) && L256 >= 128 && N >= 4096;
     const size_t gs_elems = (size_t)h->D * M * B;
-    h->os_fs = h->cfg.reserved[2] == 0 && !fast256_will_run && gs_elems * sizeof(float2) <= ((size_t)256 << 20);
+    const bool fs_form = h->cfg.reserved[2] == 0 || h->cfg.reserved[2] == 3;     // 3 = shifted filters, bank never factorised
+    h->os_fs = fs_form && !fast256_will_run && gs_elems * sizeof(float2) <= ((size_t)256 << 20);
     if (int rc = alloc_os_lane(h, 0)) return rc;
     if (h->os_fs) {
         if (int rc = dev_alloc(h, &h->d_gs_os, gs_elems)) return rc;
@@ -501,6 +568,29 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
                                                                                           best, h->D, M);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    // Factorised bank (bank_factor.cu): R transforms per (bin, block) item instead of M when the M filters are combinations
+    // of R < M basis segments (the reference's FSK-2 / CC11xx bank: R = 2, M = 8).
+    if (h->os_fs && h->cfg.reserved[2] == 0 && best >= 10 && best <= 12 && M >= 2) {
+        std::vector<int32_t> sel((size_t)M * PCS_FB_MAX_SEG);
+        std::vector<float> coef((size_t)2 * h->D * M * PCS_FB_MAX_SEG), spec(((size_t)2 * h->D * PCS_FB_MAX_BASIS) << best);
+        int32_t fS = 0, fJ = 0, fR = 0;
+        if (int rc = pcs_factorise_bank(masks_host, N, M, h->Lpos, h->Lneg, h->h_shifts.data(), h->D, best, &fS, &fJ, &fR, sel.data(),
+                                        coef.data(), spec.data()))
+            return rc;
+        int max_smem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
+        if (fR > 0 && fb_smem_bytes(best, fR, M) <= (size_t)max_smem) {
+            const size_t nb = ((size_t)h->D * fR) << best, nc = (size_t)h->D * M * fJ, ns = (size_t)M * fJ;
+            if (int rc = dev_alloc(h, &h->d_fb_basis, nb)) return rc;
+            if (int rc = dev_alloc(h, &h->d_fb_coef, nc)) return rc;
+            if (int rc = dev_alloc(h, &h->d_fb_sel, ns)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(h->d_fb_basis, spec.data(), sizeof(float2) * nb, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_fb_coef, coef.data(), sizeof(float2) * nc, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_fb_sel, sel.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->fb = true; h->fb_S = fS; h->fb_J = fJ; h->fb_R = fR;
+        }
     }
     return 0;
 }
@@ -876,6 +966,12 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
     return PCS_OK;
 }
 
+int pcs_get_bank_factor(const pcs_handle* h, int32_t out[4]) {
+    if (!h || !out) return fail(PCS_ERR_INVALID, "null argument");
+    out[0] = h->fb && !h->fast256 ? 1 : 0; out[1] = h->fb_S; out[2] = h->fb_J; out[3] = h->fb_R;
+    return PCS_OK;
+}
+
 // ---- enqueue helpers (no synchronisation) -------------------------------------------------------------
 // a4 (dem_base:557).  Only the spectrum bins computeSNR averages are ever consumed per chunk (the search works on the
 // time-domain chunk), so the hot path runs pass 1 of the four-step transform here and spectrum_bins_kernel finishes
@@ -1065,7 +1161,7 @@ static int enqueue_search_local(pcs_handle* h) {
     p.twp = twp;
     {
         StageTimer t(h, PCS_STAGE_SEARCH);
-        if (int rc = launch_search_os(h, p, false)) return rc;
+        if (int rc = h->fb ? launch_search_fb(h, p) : launch_search_os(h, p, false)) return rc;
     }
     StageTimer t2(h, PCS_STAGE_REDUCE);
     const int DM = Dl * h->M;

@@ -19,7 +19,7 @@ world_size-2 ``gloo`` tests in ``tests/test_sharded_cpu.py`` run them without a 
 from collections import deque
 
 SRC_DEVICE, SRC_HOST = 1, 2          # include/pycusdr_b200.h: PCS_SRC_DEVICE / PCS_SRC_HOST
-RESULT_STAGES = 4                    # result stages the engine keeps per owner (csrc/shard.inc: PCS_SHARD_STAGES)
+RESULT_STAGES = 8                    # result stages the engine keeps per owner (csrc/shard.inc: PCS_SHARD_STAGES)
 
 
 def bin_partition(num_bins, world):
@@ -46,7 +46,7 @@ class ShardedStream:
     oldest one is collected (at most ``RESULT_STAGES - 1``): collecting late keeps the host off the device's critical
     path -- by the time chunk ``c`` is fetched, ``lag * world`` later chunks have been enqueued."""
 
-    def __init__(self, engine, rank, world, all_gather, ring=0, lag=RESULT_STAGES - 1):
+    def __init__(self, engine, rank, world, all_gather, ring=0, lag=3):
         if not 0 <= lag < RESULT_STAGES:
             raise ValueError(f"lag must be in [0, {RESULT_STAGES - 1}]")
         self.engine, self.rank, self.world, self.lag = engine, rank, world, lag

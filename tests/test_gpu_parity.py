@@ -273,6 +273,66 @@ def test_generic_kernel_forms_agree(log2_block):
     assert (ra.shift, ra.low_idx, ra.high_idx) == (rb.shift, rb.low_idx, rb.high_idx)
 
 
+@pytest.mark.parametrize("cfg,blockSize,log2_block,sjr", [("CC11xx.json", 16, 0, (128, 3, 2)), ("CC11xx.json", 14, 12, (128, 3, 2)),
+                                                         ("benchmark/bench_FSK.json", 14, 10, (16, 3, 2))])
+def test_factorised_bank_matches_the_unfactorised_search(cfg, blockSize, log2_block, sjr):
+    """search_fb_kernel (R = 2 transforms per item + J-term combinations; bank_factor.cu) against search_os_kernel on the
+    unfactorised per-bin spectra (search_form = 3): same energies and peaks to fp32 rounding, same estimate, and against
+    the oracle <= 1e-4.  A slice of the bins (sharding) is bit-identical to the same rows of the full search."""
+    conf = conf_variant(cfg, blockSize=blockSize, doppCarrierSteps=24, noise_measure_offset_Hz=30000)
+    demA, orc = _demods(conf, fused=False, log2_block=log2_block)
+    demB, _ = _demods(conf, fused=False, log2_block=log2_block, search_form=3)
+    assert demA._engine.bank_factor() == (1,) + sjr and demB._engine.bank_factor()[0] == 0
+    sps = conf["Radios"]["Rx"][RADIO]["samplesPerSym"]
+    x = _noise_chunk(2 ** blockSize, 17, with_packet="FSK" if sps == 16 else None, sps=sps)
+    if sps != 16:       # CC11xx: an FSK-2 burst at the radio's offset so that the tables are not noise only
+        bits = S.createBitSequence(60, seed=5)
+        sig = S.modulateFSK(bits, sps)[: 2 ** blockSize - 512].astype(np.complex64)
+        fs = conf["Radios"]["Rx"][RADIO]["baud"] * sps
+        f0 = conf["Radios"]["Rx"][RADIO]["frequencyOffset_Hz"] + 3000.0
+        x[256:256 + len(sig)] += 2 * sig * np.exp(2j * np.pi * f0 / fs * np.arange(len(sig))).astype(np.complex64)
+    out = []
+    for dem in (demA, demB):
+        dem.get_signalBufferHostPointer()[:] = x
+        dem.uploadToGPU(dem.get_signalBufferHostPointer())
+        res, E = dem._engine.search()
+        v, o = dem._engine.peaks()
+        out.append((res, E.copy(), v.copy(), o.copy()))
+    (ra, Ea, va, oa), (rb, Eb, vb, ob) = out
+    assert rel_err(Ea, Eb) < 5e-6 and rel_err(va, vb) < 5e-6 and np.mean(oa != ob) <= 0.02
+    assert (ra.shift, ra.low_idx, ra.high_idx) == (rb.shift, rb.low_idx, rb.high_idx)
+    Eo, pv, po = O.search_energy(O.forward_fft(x), orc.masks, orc.doppCyperSymNorm, orc.SUM_ALL_MASKS_PYTHON, want_peaks=True)
+    assert rel_err(Ea, Eo) < 1e-4 and rel_err(va, pv) < 1e-4
+    # bin slices: rows [lo, hi) on their own == the same rows of the full table
+    eng = demA._engine
+    import torch
+    dev = []
+    for ptr, typestr in zip(eng.shard_buffers(), ("<f4", "<f4", "<i4")):
+        class _W:
+            __cuda_array_interface__ = {"shape": (eng.D, eng.M), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev.append(torch.as_tensor(_W(), device="cuda:0"))
+
+    def tables():
+        torch.cuda.synchronize()
+        got = [t.cpu().numpy().copy() for t in dev]
+        for t in dev:
+            t.zero_()
+        torch.cuda.synchronize()
+        return got
+
+    eng.upload()
+    eng.enqueue_search_local()
+    E, v, o = tables()
+    for lo, hi in ((0, 9), (9, 25)):
+        eng.set_bin_range(lo, hi)
+        eng.upload()
+        eng.enqueue_search_local()
+        Es, vs, os_ = tables()
+        np.testing.assert_array_equal(Es[lo:hi], E[lo:hi])
+        np.testing.assert_array_equal(vs[lo:hi], v[lo:hi])
+        np.testing.assert_array_equal(os_[lo:hi], o[lo:hi])
+
+
 @pytest.mark.parametrize("log2_block", [0, 10])
 def test_search_bin_range_rows_equal_the_full_table(log2_block):
     """Bin sharding: rows [lo, hi) searched on their own are bit-identical to the same rows of the full search."""
