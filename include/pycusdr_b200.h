@@ -59,7 +59,7 @@ typedef struct {
     int32_t log2_block;              /* 0 = choose; else force the overlap-save block size 2**log2_block */
     int32_t snr_window;              /* half width of the computeSNR windows (5)    dem_base:620 */
     int32_t reserved[3];             /* tuning knobs, all 0 by default.  [0] bit 0: 1 = never replay the per-chunk sequence as a
-                                        CUDA graph, bit 1: 96-register build of the shifted-filter kernel (20 warps per SM); [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
+                                        CUDA graph, bit 1: 96-register build of the shifted-filter kernel (20 warps per SM), bit 2: factorised bank without shared partial sums; [1] bits 0-7: groups per CTA of the 256-point search kernel (0 = 8; 4, 16), bits
                                         8+: (bin, block) items per CTA of the shifted-filter search kernel (0 = 64); [2] form of the
                                         256-point search: 0 = shifted filters (block spectra shared by all bins), 1 / 2 = rotate the
                                         chunk per bin with the block spectrum in shared memory / registers (comparison variants), 3 = shifted
@@ -210,7 +210,10 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info);
 int pcs_factorise_bank(const float* masks /* complex64[M*nfft] */, int32_t nfft, int32_t num_masks, int32_t support_pos,
                        int32_t support_neg, const int32_t* shifts, int32_t num_shifts, int32_t log2_block, int32_t* seg_len,
                        int32_t* num_seg, int32_t* num_basis, int32_t* sel_out, float* coef_out, float* basis_spec_out);
-/* What the handle's search uses: out[0] = 1 when the factorised bank is active, out[1..3] = S, J, R. */
+/* What the handle's search uses: out[0] = 0 unfactorised, 1 factorised (general form: selectors read at run time), 2 = a
+ * complete binary bank (R = 2, the M = 2^J selector rows all different: static selection, combinations from registers), 3 = and
+ * the coefficient of segment j depends on the selectors of segments 0..j only (partial sums shared between filters with
+ * the same prefix; an FSK-2 bank); out[1..3] = S, J, R. */
 int pcs_get_bank_factor(const pcs_handle* h, int32_t out[4]);
 
 /* Kernel launch counter (all launches issued through this handle since creation). */

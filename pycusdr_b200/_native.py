@@ -493,7 +493,7 @@ class Engine:
 
     def __init__(self, *, device, nfft, num_dopplers, element_offset, shifts, masks, window_width, sum_all_masks,
                  code_search_mask_offset, samples_per_sym, path=PATH_AUTO, log2_block=0, snr_window=5, use_graph=True, groups_per_cta=0, xb_smem=False,
-                 search_form=0, items_per_cta=0, warps20=False):
+                 search_form=0, items_per_cta=0, warps20=False, fb_tree=True):
         self.lib = load()
         shifts = np.ascontiguousarray(shifts, dtype=np.int32)
         masks = np.ascontiguousarray(masks, dtype=np.complex64)
@@ -503,7 +503,7 @@ class Engine:
             raise ValueError("shifts must have num_dopplers + element_offset entries")
         cfg = Config(ABI_VERSION, device, nfft, num_dopplers, element_offset, masks.shape[0], window_width,
                      int(bool(sum_all_masks)), code_search_mask_offset, samples_per_sym, path, log2_block, snr_window)
-        cfg.reserved[0] = (0 if use_graph else 1) | (2 if warps20 else 0)   # bit 0: no CUDA graph; bit 1: 20-warp build
+        cfg.reserved[0] = (0 if use_graph else 1) | (2 if warps20 else 0) | (0 if fb_tree else 4)   # bit 0: no CUDA graph; bit 1: 20-warp build; bit 2: factorised bank without shared partial sums
         cfg.reserved[1] = int(groups_per_cta) | (int(items_per_cta) << 8)    # tuning knobs of the 256-point search kernels
         # form of the 256-point search: 0 shifted filters (default), 1 rotate + block spectrum in shared memory, 2 rotate
         cfg.reserved[2] = 1 if xb_smem else int(search_form)
@@ -664,7 +664,8 @@ class Engine:
 
     # -- bin sharding ----------------------------------------------------------------------------
     def bank_factor(self):
-        """(active, S, J, R) of the factorised filter bank the generic search uses (``pcs_get_bank_factor``)."""
+        """(form, S, J, R) of the factorised filter bank the generic search uses (``pcs_get_bank_factor``): form 0 = not
+        factorised, 1 = general, 2 = complete binary bank, 3 = complete binary bank with shared partial sums."""
         out = np.zeros(4, dtype=np.int32)
         self._check(load().pcs_get_bank_factor(self._h, _ptr(out)))
         return tuple(int(v) for v in out)

@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
 struct FbSearchParams {
     const float2* __restrict__ xbs;     // [nblk][B] block spectra of the unrotated chunk
     const float2* __restrict__ gbasis;  // [D][R][B] per-bin basis spectra
-    const float2* __restrict__ coef;    // [D][M][J]
-    const int* __restrict__ sel;        // [M][J] basis index of every segment
+    const float2* __restrict__ coef;    // [D][M][J]  (complete binary bank: filters in code order)
+    const int* __restrict__ sel;        // [M][J] basis index of every segment  (complete binary bank: [M] code -> mask)
     const float2* __restrict__ tw;      // [B] exp(-2 pi i t / B)
     float* __restrict__ psum;           // [D][M][nblk]
     float* __restrict__ pmax;           // [D][M][nblk]
@@ -267,19 +267,31 @@ PCS_DEVINL float2 cfma(float2 c, float2 a, float2 y) {      // y + c a: two FFMA
     return __ffma2_rn(make_float2(c.y, c.y), make_float2(-a.y, a.x), t);
 }
 
-template <int LOGB, int G, int J>
-__global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T <= 128) ? 3 : 1) search_fb_kernel(FbSearchParams p) {
+// CB = "complete binary bank": R = 2 basis filters and M = 2^J filters whose selectors enumerate all 2^J sequences (what an
+// FSK-2 bank is).  The host then orders the filters by code = sum_j sel[m][j] 2^j (coef in code order, sel = code -> mask),
+// every selection is static, and the combination runs from registers: per pair of outputs the 2 J values u_r[i + j S] are
+// loaded ONCE (2 J 128-bit loads instead of M J) and feed 2 M independent multiply-add chains.  (The general form below
+// re-reads shared memory per (mask, segment): ncu on C1 showed its epilogue at 67 % of the kernel, 1.65 IPC, bound by the
+// latency of its short dependent chains.)
+template <int LOGB, int G, int J, int CBM>
+__global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T <= 128) ? (CBM ? 4 : 3) : (CBM && G * FftShape<LOGB>::T <= 256) ? 2 : 1)
+    search_fb_kernel(FbSearchParams p) {
+    constexpr bool CB = CBM != 0, TREE = CBM == 2;
     using S = FftShape<LOGB>;
     constexpr int B = S::B, T = S::T, NW = (T + 31) / 32;
+    static_assert(S::NPASS == 3, "search_fb_kernel: three-pass transforms (B = 2^9 .. 2^12)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* smem = reinterpret_cast<float2*>(smem_raw);
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const size_t gstride = (size_t)3 * S::WORK + (size_t)(p.R - 1) * B;
+    // CB: three buffers in rotation (below); else work0 | work1 | xb | u_0 .. u_{R-2}
+    const size_t gstride = (size_t)3 * S::WORK + (CB ? 0 : (size_t)(p.R - 1) * B);
     float2* work0 = smem + (size_t)g * gstride;
     float2* work1 = work0 + S::WORK;
-    float2* xb = work1 + S::WORK;       // the item's block spectrum (padded layout), later u_{R-1} (natural, unpadded)
-    float2* ub = xb + S::WORK;          // u_0 .. u_{R-2}, B each
+    float2* xb = work1 + S::WORK;       // the item's block spectrum (padded layout)
+    float2* ub = xb + S::WORK;          // (not CB) u_0 .. u_{R-2}, B each; u_{R-1} goes over xb (natural, unpadded)
     float* red = reinterpret_cast<float*>(smem + (size_t)G * gstride) + (size_t)g * p.M * NW * 2;
+    float2* cs = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + (size_t)G * gstride) + (size_t)G * p.M * NW * 2) +
+                 (size_t)g * p.M * J;   // the bin's M x J coefficients
     const int bar_id = 1 + g;
 
     const long long item = (long long)blockIdx.x * G + g;
@@ -290,61 +302,175 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
         const float2* __restrict__ xs = p.xbs + (size_t)blk * B;
 #pragma unroll
         for (int r = 0; r < 16; ++r) xb[padi(t + r * T)] = __ldg(&xs[t + r * T]);
+        for (int q = t; q < p.M * J; q += T) cs[q] = __ldg(&p.coef[(size_t)d * p.M * J + q]);
     }
     group_sync<T>(bar_id);
-    for (int r = 0; r < p.R; ++r) {
-        const float2* __restrict__ gm = p.gbasis + ((size_t)d * p.R + r) * B;
-        float2* __restrict__ dst = r == p.R - 1 ? xb : ub + (size_t)r * B;
-        auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
-        auto sink = [&](int i, float2 v, int) { dst[i] = v; };
-        group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
+    const float2 *u0 = ub, *u1 = xb;    // CB: where u_0 and u_1 end up
+    if constexpr (CB) {
+        // R = 2 transforms through THREE buffers (52 KB per 2048-point group: four 128-thread CTAs per SM instead of three):
+        //   u_0:  xb x G_0 -> work0 -> work1 -> work0 (natural order);   u_1:  xb x G_1 -> work1 -> xb -> work1 (natural order)
+        // Every pass reads one buffer and writes another one that no thread still reads: the group barrier after each pass
+        // (one more than back-to-back group_fft calls need: the one after u_0's last pass frees work1) orders them.
+        const float2* __restrict__ g0 = p.gbasis + (size_t)d * 2 * B;
+        const float2* __restrict__ g1 = g0 + B;
+        auto ld0 = [&](int i) { return work0[padi(i)]; };
+        auto ld1 = [&](int i) { return work1[padi(i)]; };
+        auto ldx = [&](int i) { return xb[padi(i)]; };
+        auto st0 = [&](int i, float2 v, int) { work0[padi(i)] = v; };
+        auto st1 = [&](int i, float2 v, int) { work1[padi(i)] = v; };
+        auto stx = [&](int i, float2 v, int) { xb[padi(i)] = v; };
+        auto nat0 = [&](int i, float2 v, int) { work0[i] = v; };
+        auto nat1 = [&](int i, float2 v, int) { work1[i] = v; };
+        auto src0 = [&](int i) { return cmul(xb[padi(i)], __ldg(&g0[i])); };
+        auto src1 = [&](int i) { return cmul(xb[padi(i)], __ldg(&g1[i])); };
+        fft_pass<LOGB, 16, 0, +1>(t, p.tw, src0, st0);
+        group_sync<T>(bar_id);
+        fft_pass<LOGB, 16, 4, +1>(t, p.tw, ld0, st1);
+        group_sync<T>(bar_id);
+        fft_pass<LOGB, S::RLAST, 8, +1>(t, p.tw, ld1, nat0);
+        group_sync<T>(bar_id);
+        fft_pass<LOGB, 16, 0, +1>(t, p.tw, src1, st1);
+        group_sync<T>(bar_id);
+        fft_pass<LOGB, 16, 4, +1>(t, p.tw, ld1, stx);
+        group_sync<T>(bar_id);
+        fft_pass<LOGB, S::RLAST, 8, +1>(t, p.tw, ldx, nat1);
+        u0 = work0;
+        u1 = work1;
+    } else {
+        for (int r = 0; r < p.R; ++r) {
+            const float2* __restrict__ gm = p.gbasis + ((size_t)d * p.R + r) * B;
+            float2* __restrict__ dst = r == p.R - 1 ? xb : ub + (size_t)r * B;
+            auto src = [&](int i) { return cmul(xb[padi(i)], __ldg(&gm[i])); };
+            auto sink = [&](int i, float2 v, int) { dst[i] = v; };
+            group_fft<LOGB, +1>(work0, work1, p.tw, t, bar_id, src, sink);
+        }
     }
     group_sync<T>(bar_id);
 
     const int lo = p.Lpos, hi = p.Lpos + min(p.V, p.N - n0);     // valid outputs of the block: lo <= i < hi
     const int lane = t & 31, warp = t >> 5;
-    for (int m = 0; m < p.M; ++m) {
-        float2 c[J];
-        const float2* up[J];
+    if constexpr (CB) {
+        constexpr int MC = 1 << J;
+        // TREE: c[code][j] depends on the low j + 1 bits of the code only (FSK-2: the phase a segment starts with is set by
+        // the symbols before it), so the partial sums over segments 0..j are shared by the codes with the same prefix:
+        // 2 + 4 + .. + 2^J multiply-adds per output instead of J 2^J, and that many coefficients in registers.
+        float2 c[MC][J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            c[j] = __ldg(&p.coef[((size_t)d * p.M + m) * J + j]);
-            const int r = __ldg(&p.sel[m * J + j]);
-            up[j] = (r == p.R - 1 ? xb : ub + (size_t)r * B) + j * p.S;
-        }
-        float sum = 0.f, best = 0.f;
+        for (int code = 0; code < MC; ++code)
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (!TREE || code < (2 << j)) c[code][j] = cs[code * J + j];
+        float sum[MC], best[MC];
+#pragma unroll
+        for (int code = 0; code < MC; ++code) sum[code] = best[code] = 0.f;
+        const int nq = (hi + 2 * T - 1) / (2 * T);      // steps that hold a valid output (uniform over the group)
+        const int last = (hi - 1) & ~1;                 // last pair with a valid output: loads beyond it are clamped to it
 #pragma unroll
         for (int q = 0; q < B / (2 * T); ++q) {
-            const int i0 = 2 * (t + T * q);
-            if (i0 < hi) {
-                float4 a = *reinterpret_cast<const float4*>(up[0] + i0);
-                float2 y0 = cmul(c[0], make_float2(a.x, a.y)), y1 = cmul(c[0], make_float2(a.z, a.w));
+            if (q < nq) {
+                const int i0 = 2 * (t + T * q), ic = min(i0, last);
+                float4 P[J][2];
 #pragma unroll
-                for (int j = 1; j < J; ++j) {
-                    a = *reinterpret_cast<const float4*>(up[j] + i0);
-                    y0 = cfma(c[j], make_float2(a.x, a.y), y0);
-                    y1 = cfma(c[j], make_float2(a.z, a.w), y1);
+                for (int j = 0; j < J; ++j) {
+                    P[j][0] = *reinterpret_cast<const float4*>(u0 + ic + j * p.S);
+                    P[j][1] = *reinterpret_cast<const float4*>(u1 + ic + j * p.S);
                 }
-                const float m0 = i0 >= lo ? cabs2(y0) : 0.f;
-                const float m1 = (i0 + 1 >= lo && i0 + 1 < hi) ? cabs2(y1) : 0.f;
-                sum += m0;
-                sum += m1;
-                best = fmaxf(best, fmaxf(m0, m1));
+                const bool v0 = i0 >= lo && i0 < hi, v1 = i0 + 1 >= lo && i0 + 1 < hi;
+                float2 y0[MC], y1[MC];
+                if constexpr (TREE) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+#pragma unroll
+                        for (int pre = (2 << j) - 1; pre >= 0; --pre) {      // downwards: y[pre] of level j - 1 is read before it is replaced
+                            const float4 a = P[j][(pre >> j) & 1];
+                            if (j == 0) {
+                                y0[pre] = cmul(c[pre][0], make_float2(a.x, a.y));
+                                y1[pre] = cmul(c[pre][0], make_float2(a.z, a.w));
+                            } else {
+                                y0[pre] = cfma(c[pre][j], make_float2(a.x, a.y), y0[pre & ((1 << j) - 1)]);
+                                y1[pre] = cfma(c[pre][j], make_float2(a.z, a.w), y1[pre & ((1 << j) - 1)]);
+                            }
+                        }
+                } else {
+#pragma unroll
+                    for (int code = 0; code < MC; ++code) {
+                        float4 a = P[0][code & 1];
+                        y0[code] = cmul(c[code][0], make_float2(a.x, a.y));
+                        y1[code] = cmul(c[code][0], make_float2(a.z, a.w));
+#pragma unroll
+                        for (int j = 1; j < J; ++j) {
+                            a = P[j][(code >> j) & 1];
+                            y0[code] = cfma(c[code][j], make_float2(a.x, a.y), y0[code]);
+                            y1[code] = cfma(c[code][j], make_float2(a.z, a.w), y1[code]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int code = 0; code < MC; ++code) {
+                    const float m0 = v0 ? cabs2(y0[code]) : 0.f, m1 = v1 ? cabs2(y1[code]) : 0.f;
+                    sum[code] += m0;
+                    sum[code] += m1;
+                    best[code] = fmaxf(best[code], fmaxf(m0, m1));
+                }
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        for (int code = 0; code < MC; ++code) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum[code] += __shfl_xor_sync(0xffffffffu, sum[code], o);
+                best[code] = fmaxf(best[code], __shfl_xor_sync(0xffffffffu, best[code], o));
+            }
+            if (lane == 0) {
+                float* r = red + ((size_t)code * NW + warp) * 2;
+                r[0] = sum[code];
+                r[1] = best[code];
+            }
         }
-        if (lane == 0) {
-            float* r = red + ((size_t)m * NW + warp) * 2;
-            r[0] = sum;
-            r[1] = best;
+    } else {
+        for (int m = 0; m < p.M; ++m) {
+            float2 c[J];
+            const float2* up[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                c[j] = cs[m * J + j];
+                const int r = __ldg(&p.sel[m * J + j]);
+                up[j] = (r == p.R - 1 ? xb : ub + (size_t)r * B) + j * p.S;
+            }
+            float sum = 0.f, best = 0.f;
+#pragma unroll
+            for (int q = 0; q < B / (2 * T); ++q) {
+                const int i0 = 2 * (t + T * q);
+                if (i0 < hi) {
+                    float4 a = *reinterpret_cast<const float4*>(up[0] + i0);
+                    float2 y0 = cmul(c[0], make_float2(a.x, a.y)), y1 = cmul(c[0], make_float2(a.z, a.w));
+#pragma unroll
+                    for (int j = 1; j < J; ++j) {
+                        a = *reinterpret_cast<const float4*>(up[j] + i0);
+                        y0 = cfma(c[j], make_float2(a.x, a.y), y0);
+                        y1 = cfma(c[j], make_float2(a.z, a.w), y1);
+                    }
+                    const float m0 = i0 >= lo ? cabs2(y0) : 0.f;
+                    const float m1 = (i0 + 1 >= lo && i0 + 1 < hi) ? cabs2(y1) : 0.f;
+                    sum += m0;
+                    sum += m1;
+                    best = fmaxf(best, fmaxf(m0, m1));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            }
+            if (lane == 0) {
+                float* r = red + ((size_t)m * NW + warp) * 2;
+                r[0] = sum;
+                r[1] = best;
+            }
         }
     }
     group_sync<T>(bar_id);
-    for (int m = t; m < p.M; m += T) {
+    for (int m = t; m < p.M; m += T) {        // CB: m is a code, sel[code] its mask
         float sum = 0.f, best = 0.f;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -352,7 +478,8 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
             sum += r[0];
             best = fmaxf(best, r[1]);
         }
-        const size_t o = ((size_t)d * p.M + m) * p.nblk + blk;
+        const int mask = CB ? __ldg(&p.sel[m]) : m;
+        const size_t o = ((size_t)d * p.M + mask) * p.nblk + blk;
         p.psum[o] = sum;
         p.pmax[o] = best;
     }

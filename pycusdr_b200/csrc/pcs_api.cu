@@ -120,6 +120,8 @@ struct pcs_handle {
     float2* d_gs_os = nullptr;         // per-bin filter spectra of the generic kernel's shifted-filter form (natural order)
     // factorised filter bank (bank_factor.cu): R basis filters, J segments of S taps per filter; search_fb_kernel
     bool fb = false;
+    int fb_complete = 0;     // 1: R = 2 and the M = 2^J selector rows are all different (an FSK-2 bank); 2: and the coefficient of
+                             // segment j depends on the selectors of segments 0..j only (shared partial sums)
     int fb_S = 0, fb_J = 0, fb_R = 0;
     float2 *d_fb_basis = nullptr, *d_fb_coef = nullptr;   // [D][R][B], [D][M][J]
     int* d_fb_sel = nullptr;                               // [M][J]
@@ -384,7 +386,7 @@ static int launch_search_os_t(pcs_handle* h, const OsSearchParams& p, bool locat
 
 // Factorised bank: block spectra (as for the shifted-filter form), then search_fb_kernel with G = max(1, 2048 / B) groups
 // per CTA (three 128-thread CTAs per SM up to B = 2048).
-template <int LOGB, int GBS, int G, int J>
+template <int LOGB, int GBS, int G, int J, int CB>
 static int launch_search_fb_tj(pcs_handle* h, const OsSearchParams& p) {
     using S = FftShape<LOGB>;
     constexpr int NW = (S::T + 31) / 32;
@@ -404,9 +406,9 @@ static int launch_search_fb_tj(pcs_handle* h, const OsSearchParams& p) {
     q.coef = h->d_fb_coef + (size_t)h->bin_lo * h->M * J;
     q.sel = h->d_fb_sel;
     q.N = p.N; q.D = p.D; q.M = p.M; q.nblk = p.nblk; q.V = p.V; q.Lpos = p.Lpos; q.R = h->fb_R; q.S = h->fb_S;
-    const size_t smem = (size_t)G * ((size_t)3 * S::WORK + (size_t)(q.R - 1) * S::B) * sizeof(float2) +
-                        (size_t)G * p.M * NW * 2 * sizeof(float);
-    auto kern = search_fb_kernel<LOGB, G, J>;
+    const size_t smem = (size_t)G * ((size_t)3 * S::WORK + (CB ? 0 : (size_t)(q.R - 1) * S::B)) * sizeof(float2) +
+                        (size_t)G * p.M * NW * 2 * sizeof(float) + (size_t)G * p.M * J * sizeof(float2);
+    auto kern = search_fb_kernel<LOGB, G, J, CB>;
     static size_t configured[PCS_MAX_DEVICES] = {};
     if (configured[h->cfg.device] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -424,15 +426,19 @@ static int launch_search_fb_tj(pcs_handle* h, const OsSearchParams& p) {
 template <int LOGB, int GBS, int G>
 static int launch_search_fb_t(pcs_handle* h, const OsSearchParams& p) {
     switch (h->fb_J) {
-        case 2: return launch_search_fb_tj<LOGB, GBS, G, 2>(h, p);
-        case 3: return launch_search_fb_tj<LOGB, GBS, G, 3>(h, p);
-        case 4: return launch_search_fb_tj<LOGB, GBS, G, 4>(h, p);
+        case 2: return h->fb_complete == 2   ? launch_search_fb_tj<LOGB, GBS, G, 2, 2>(h, p)
+                       : h->fb_complete == 1 ? launch_search_fb_tj<LOGB, GBS, G, 2, 1>(h, p)
+                                             : launch_search_fb_tj<LOGB, GBS, G, 2, 0>(h, p);
+        case 3: return h->fb_complete == 2   ? launch_search_fb_tj<LOGB, GBS, G, 3, 2>(h, p)
+                       : h->fb_complete == 1 ? launch_search_fb_tj<LOGB, GBS, G, 3, 1>(h, p)
+                                             : launch_search_fb_tj<LOGB, GBS, G, 3, 0>(h, p);
+        case 4: return launch_search_fb_tj<LOGB, GBS, G, 4, 0>(h, p);
     }
     return fail(PCS_ERR_INVALID, "factorised bank with %d segments", h->fb_J);
 }
 static size_t fb_smem_bytes(int logB, int R, int M) {
     const size_t B = (size_t)1 << logB, work = B + (B >> 4), T = B / 16, G = std::max<size_t>(1, 2048 / B), NW = (T + 31) / 32;
-    return G * (3 * work + (size_t)(R - 1) * B) * sizeof(float2) + G * M * NW * 2 * sizeof(float);
+    return G * (3 * work + (size_t)(R - 1) * B) * sizeof(float2) + G * M * NW * 2 * sizeof(float) + G * M * PCS_FB_MAX_SEG * sizeof(float2);
 }
 static int launch_search_fb(pcs_handle* h, const OsSearchParams& p) {
     switch (h->logB) {
@@ -582,6 +588,34 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
         if (fR > 0 && fb_smem_bytes(best, fR, M) <= (size_t)max_smem) {
             const size_t nb = ((size_t)h->D * fR) << best, nc = (size_t)h->D * M * fJ, ns = (size_t)M * fJ;
+            // complete binary bank: filters in code order (code = sum_j sel[m][j] 2^j), sel becomes code -> mask
+            std::vector<int32_t> code_mask((size_t)M, -1);
+            bool complete = fR == 2 && fJ <= 3 && M == (1 << fJ);
+            for (int m = 0; m < M && complete; ++m) {
+                int code = 0;
+                for (int j = 0; j < fJ; ++j) code |= sel[(size_t)m * fJ + j] << j;
+                if (code_mask[code] >= 0) complete = false;
+                code_mask[code] = m;
+            }
+            if (complete) {
+                std::vector<float> cc(coef.size());
+                for (int d = 0; d < h->D; ++d)
+                    for (int code = 0; code < M; ++code)
+                        memcpy(&cc[2 * (((size_t)d * M + code) * fJ)], &coef[2 * (((size_t)d * M + code_mask[code]) * fJ)], sizeof(float) * 2 * fJ);
+                coef.swap(cc);
+                std::copy(code_mask.begin(), code_mask.end(), sel.begin());
+            }
+            h->fb_complete = complete ? 1 : 0;
+            if (complete && h->cfg.reserved[0] & 4) complete = false;      // experiment knob: no shared partial sums
+            for (size_t d = 0; d < (size_t)h->D && complete; ++d)
+                for (int code = 0; code < M && complete; ++code)
+                    for (int j = 0; j + 1 < fJ; ++j) {
+                        const float* a = &coef[2 * ((d * M + code) * fJ + j)];
+                        const float* b = &coef[2 * ((d * M + (code & ((2 << j) - 1))) * fJ + j)];
+                        const float tol = 1e-6f * (fabsf(b[0]) + fabsf(b[1]));
+                        if (fabsf(a[0] - b[0]) > tol || fabsf(a[1] - b[1]) > tol) { complete = false; break; }
+                    }
+            if (complete) h->fb_complete = 2;
             if (int rc = dev_alloc(h, &h->d_fb_basis, nb)) return rc;
             if (int rc = dev_alloc(h, &h->d_fb_coef, nc)) return rc;
             if (int rc = dev_alloc(h, &h->d_fb_sel, ns)) return rc;
@@ -968,7 +1002,7 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info) {
 
 int pcs_get_bank_factor(const pcs_handle* h, int32_t out[4]) {
     if (!h || !out) return fail(PCS_ERR_INVALID, "null argument");
-    out[0] = h->fb && !h->fast256 ? 1 : 0; out[1] = h->fb_S; out[2] = h->fb_J; out[3] = h->fb_R;
+    out[0] = h->fb && !h->fast256 ? 1 + h->fb_complete : 0; out[1] = h->fb_S; out[2] = h->fb_J; out[3] = h->fb_R;
     return PCS_OK;
 }
 

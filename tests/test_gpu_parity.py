@@ -282,7 +282,7 @@ def test_factorised_bank_matches_the_unfactorised_search(cfg, blockSize, log2_bl
     conf = conf_variant(cfg, blockSize=blockSize, doppCarrierSteps=24, noise_measure_offset_Hz=30000)
     demA, orc = _demods(conf, fused=False, log2_block=log2_block)
     demB, _ = _demods(conf, fused=False, log2_block=log2_block, search_form=3)
-    assert demA._engine.bank_factor() == (1,) + sjr and demB._engine.bank_factor()[0] == 0
+    assert demA._engine.bank_factor() == (3,) + sjr and demB._engine.bank_factor()[0] == 0      # FSK-2: complete, shared prefixes
     sps = conf["Radios"]["Rx"][RADIO]["samplesPerSym"]
     x = _noise_chunk(2 ** blockSize, 17, with_packet="FSK" if sps == 16 else None, sps=sps)
     if sps != 16:       # CC11xx: an FSK-2 burst at the radio's offset so that the tables are not noise only
@@ -331,6 +331,58 @@ def test_factorised_bank_matches_the_unfactorised_search(cfg, blockSize, log2_bl
         np.testing.assert_array_equal(Es[lo:hi], E[lo:hi])
         np.testing.assert_array_equal(vs[lo:hi], v[lo:hi])
         np.testing.assert_array_equal(os_[lo:hi], o[lo:hi])
+
+
+@pytest.mark.parametrize("bank", ["incomplete", "three_tones", "two_segments", "two_segments_no_tree", "cc11xx_no_tree"])
+def test_factorised_bank_general_form(bank):
+    """Banks that factorise but are not a complete binary bank take search_fb_kernel's general epilogue (selectors read at
+    run time): 7 of the 8 CC11xx templates; 9 two-segment templates over three tones (R = 3); the 4 two-symbol FSK-2
+    templates (complete, J = 2).  Against the unfactorised search on the same spectra, and against the oracle."""
+    from pycusdr_b200 import _native
+    from pycusdr_b200.protocol.FSK2_base import fsk_phase_templates
+    N, sps = 2 ** 14, 128
+    if bank == "incomplete":
+        pats = [np.array([(k >> 2) & 1, (k >> 1) & 1, k & 1]) for k in range(8) if k != 5]
+        tmpl = fsk_phase_templates(pats, sps, 0.5)
+        want = (1, 128, 3, 2)
+    elif bank.startswith("two_segments"):
+        tmpl = fsk_phase_templates([np.array([a, b]) for a in (0, 1) for b in (0, 1)], sps, 0.5)
+        want = (3 if bank == "two_segments" else 2, 128, 2, 2)
+    elif bank == "cc11xx_no_tree":
+        tmpl = fsk_phase_templates([np.array([(k >> 2) & 1, (k >> 1) & 1, k & 1]) for k in range(8)], sps, 0.5)
+        want = (2, 128, 3, 2)
+    else:
+        n = np.arange(sps)
+        tones = [np.exp(2j * np.pi * f * n / sps) for f in (-1.0, 0.5, 1.5)]
+        tmpl = [np.concatenate((tones[a], np.exp(0.3j * (a + 2 * b)) * tones[b])) for a in range(3) for b in range(3)]
+        want = (1, 128, 2, 3)
+    M = len(tmpl)
+    masks = np.zeros((M, N), dtype=np.complex128)
+    for m, tp in enumerate(tmpl):
+        masks[m, :len(tp)] = tp
+    masks = np.conj(np.fft.fft(masks, axis=1)).astype(np.complex64)        # protocolBase._pad_and_conj_fft
+    D = 12
+    shifts = ((np.arange(D) - D // 2) * 37) % N
+    kw = dict(device=0, nfft=N, num_dopplers=D, element_offset=0, shifts=shifts, masks=masks, window_width=7,
+              sum_all_masks=True, code_search_mask_offset=0, samples_per_sym=sps)
+    engA, engB = _native.Engine(fb_tree=not bank.endswith("no_tree"), **kw), _native.Engine(search_form=3, **kw)
+    assert engA.bank_factor() == want and engB.bank_factor()[0] == 0
+    rng = np.random.RandomState(23)
+    x = ((rng.randn(N) + 1j * rng.randn(N)) * 0.5).astype(np.complex64)
+    x[300:300 + len(tmpl[2])] += (3 * tmpl[2] * np.exp(2j * np.pi * 37 * 2 * np.arange(len(tmpl[2])) / N)).astype(np.complex64)
+    out = []
+    for eng in (engA, engB):
+        eng.host_buffer[:] = x
+        eng.upload()
+        res, E = eng.search()
+        v, o = eng.peaks()
+        out.append((E.copy(), v.copy(), o.copy()))
+    (Ea, va, oa), (Eb, vb, ob) = out
+    assert rel_err(Ea, Eb) < 5e-6 and rel_err(va, vb) < 5e-6 and np.mean(oa != ob) <= 0.02
+    Eo, pv, po = O.search_energy(O.forward_fft(x), masks, shifts, True, want_peaks=True)
+    assert rel_err(Ea, Eo) < 1e-4 and rel_err(va, pv) < 1e-4
+    engA.close()
+    engB.close()
 
 
 @pytest.mark.parametrize("log2_block", [0, 10])
