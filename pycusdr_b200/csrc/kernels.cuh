@@ -298,13 +298,13 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
     if (item >= (long long)p.nblk * p.D) return;      // whole group leaves (own barrier id)
     const int blk = (int)(item % p.nblk), d = (int)(item / p.nblk);
     const int n0 = blk * p.V;
-    {
-        const float2* __restrict__ xs = p.xbs + (size_t)blk * B;
+    const float2* __restrict__ xs = p.xbs + (size_t)blk * B;
+    for (int q = t; q < p.M * J; q += T) cs[q] = __ldg(&p.coef[(size_t)d * p.M * J + q]);
+    if constexpr (!CB) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) xb[padi(t + r * T)] = __ldg(&xs[t + r * T]);
-        for (int q = t; q < p.M * J; q += T) cs[q] = __ldg(&p.coef[(size_t)d * p.M * J + q]);
+        group_sync<T>(bar_id);
     }
-    group_sync<T>(bar_id);
     const float2 *u0 = ub, *u1 = xb;    // CB: where u_0 and u_1 end up
     if constexpr (CB) {
         // R = 2 transforms through THREE buffers (52 KB per 2048-point group: four 128-thread CTAs per SM instead of three):
@@ -321,7 +321,13 @@ __global__ void __launch_bounds__(G * FftShape<LOGB>::T, (G * FftShape<LOGB>::T 
         auto stx = [&](int i, float2 v, int) { xb[padi(i)] = v; };
         auto nat0 = [&](int i, float2 v, int) { work0[i] = v; };
         auto nat1 = [&](int i, float2 v, int) { work1[i] = v; };
-        auto src0 = [&](int i) { return cmul(xb[padi(i)], __ldg(&g0[i])); };
+        // pass 0 reads inputs t + r T: exactly the elements of the block spectrum this thread would stage, so u_0's pass 0
+        // takes them straight from global memory and parks them in xb for u_1's pass 0 (same thread: no barrier in between)
+        auto src0 = [&](int i) {
+            const float2 xv = __ldg(&xs[i]);
+            xb[padi(i)] = xv;
+            return cmul(xv, __ldg(&g0[i]));
+        };
         auto src1 = [&](int i) { return cmul(xb[padi(i)], __ldg(&g1[i])); };
         fft_pass<LOGB, 16, 0, +1>(t, p.tw, src0, st0);
         group_sync<T>(bar_id);

@@ -24,10 +24,20 @@ dev = torch.from_numpy(W.chunks_from_stream(W.build_stream(conf, mod, ring, seed
 torch.cuda.synchronize()
 dem = UHF.Demodulator(conf, P, W.RADIO)
 sh = sharded.ShardedStream(dem._engine, 0, 1, lambda o: [o], lag=int(os.environ.get("LAG", "2")))
-for i in range(n):
+import time
+for i in range(16):                # warm-up: first launches, lazy allocations
     sh.submit(dev[i % ring].data_ptr(), sharded.SRC_DEVICE, lambda c, out: None)
 sh.drain(lambda c, out: None)
 dem._engine.shard_sync()
+t0 = time.perf_counter()
+for i in range(n):
+    sh.submit(dev[i % ring].data_ptr(), sharded.SRC_DEVICE, lambda c, out: None)
+t1 = time.perf_counter()
+sh.drain(lambda c, out: None)
+dem._engine.shard_sync()
+t2 = time.perf_counter()
+print(f"host: {n} submits (with their fetches) returned after {1e6 * (t1 - t0) / n:.1f} us per chunk; everything finished after "
+      f"{1e6 * (t2 - t0) / n:.1f} us per chunk; launches per chunk {dem._engine.launch_count / (n + 16):.1f}")
 first, t = dem._engine.shard_trace()
 print(desc, dem._engine.shard_info())
 prev_end = None
