@@ -1937,9 +1937,17 @@ struct FlagList {
     unsigned long long* dst[16];
     int n;
 };
-__global__ void flags_set_kernel(FlagList f, unsigned long long value) {
+// tagp != null (a launch replayed from a CUDA graph, whose parameters are frozen): the value is read from *tagp, which is then
+// advanced by inc for the next replay.
+__global__ void flags_set_kernel(FlagList f, unsigned long long value, unsigned long long* tagp = nullptr,
+                                 unsigned long long inc = 0ull) {
+    if (tagp) value = *tagp;
     __threadfence_system();
     if ((int)threadIdx.x < f.n) st_release_sys(f.dst[threadIdx.x], value);
+    if (tagp) {
+        __syncwarp();
+        if (threadIdx.x == 0) *tagp = value + inc;
+    }
 }
 __global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {
     // the rows were stored by the preceding kernels of this stream; make them visible system-wide, then publish
@@ -1954,15 +1962,17 @@ struct WaitList {
     unsigned long long want[20];
     int n;
 };
-__global__ void flags_wait_kernel(WaitList w, int exact, int* err, DevResult* res) {
+// tagp != null (graph replay): every non-zero `want` is replaced by *tagp.
+__global__ void flags_wait_kernel(WaitList w, int exact, int* err, DevResult* res, const unsigned long long* tagp = nullptr) {
     const int i = threadIdx.x;
     int bad = 0;
     if (i < w.n && w.want[i] != 0ull) {
+        const unsigned long long want = tagp ? *tagp : w.want[i];
         const long long t0 = clock64();
         for (;;) {
             const unsigned long long v = ld_acquire_sys(w.src[i]);
-            if (v >= w.want[i]) {
-                if (exact && v > w.want[i]) bad = 2;
+            if (v >= want) {
+                if (exact && v > want) bad = 2;
                 break;
             }
             if (clock64() - t0 > PCS_WAIT_CYCLES) { bad = 1; break; }

@@ -36,11 +36,12 @@ def _case(name):
     N, ovl = 2 ** bs, 2 ** conf["GPU"]["UHF"]["overlap"]
     if mod is None:
         from pycusdr_b200.benchmark import workloads as W
-        sig = W.build_stream(conf, None, 7, seed=seed)
+        sig = W.build_stream(conf, None, 20, seed=seed)        # 20 chunks: >= 9 owned chunks per rank on two ranks, so the
+                                                               # tail runs from its CUDA graph (captured on an instance's second use)
     else:
-        sig, _ = S.bench_stream(mod, snr, seed=seed, pre_blocks=1)
+        sig, _ = S.bench_stream(mod, snr, n_packets=3, seed=seed, pre_blocks=1)
         sig = sig[:(len(sig) // (N - ovl)) * (N - ovl)]
-        sig = sig[:12 * (N - ovl)]
+        sig = sig[:30 * (N - ovl)]      # 30 chunks: the graph-replayed tail is exercised on 1, 2 and 3 ranks
     return conf, N, ovl, np.ascontiguousarray(sig, dtype=np.complex64)
 
 
@@ -74,7 +75,7 @@ def _compare(got, want, what):
             np.testing.assert_array_equal(g[k], w[k], err_msg=f"{what} chunk {c}: {k}")
 
 
-def _run_rank(rank, world, name, kind, all_gather, send, recv, lag=2, device=0):
+def _run_rank(rank, world, name, kind, all_gather, send, recv, lag=2, device=0, before_chunk=None):
     """The per-rank loop of the sharded stream; returns {chunk: result dict} of the chunks this rank owned."""
     import torch
     from pycusdr_b200 import sharded
@@ -100,6 +101,8 @@ def _run_rank(rank, world, name, kind, all_gather, send, recv, lag=2, device=0):
     prev_tail = np.zeros(ovl, np.complex64)
     dev_keep = []
     for c in range(n_chunks):
+        if before_chunk is not None:
+            before_chunk(c, dem._engine)
         if rank == 0:
             chunk = np.concatenate((prev_tail, sig[c * step:(c + 1) * step]))
             prev_tail = chunk[-ovl:].copy()
@@ -134,6 +137,24 @@ def test_single_rank_engine_equals_the_class_api(name, kind):
     mine, owned, n = _run_rank(0, 1, name, k, lambda o: [o], None, None, lag=3)
     assert owned == set(range(n)) == set(mine) and n == len(want) >= 6
     _compare([mine[c] for c in range(n)], want, name)
+
+
+def test_graph_replayed_tail_survives_eager_chunks_in_between():
+    """The owner's tail is replayed from a CUDA graph from an instance's second use on; with per-stage profiling switched on
+    the engine falls back to eager launches, and the flag value the graph reads from device memory must be re-seeded when the
+    replays resume (chunks 11-14 eager here, graphs before and after)."""
+    from pycusdr_b200 import sharded
+    conf, N, ovl, sig = _case("gmsk_fs256")
+    want = _unsharded(conf, sig)
+
+    def toggle(c, eng):
+        if c == 11:
+            eng.set_profiling(True)
+        if c == 15:
+            eng.set_profiling(False)
+    mine, owned, n = _run_rank(0, 1, "gmsk_fs256", sharded.SRC_DEVICE, lambda o: [o], None, None, lag=5, before_chunk=toggle)
+    assert n == len(want) >= 25
+    _compare([mine[c] for c in range(n)], want, "graph / eager / graph")
 
 
 def _free_port():
