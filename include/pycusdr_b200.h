@@ -82,7 +82,7 @@ typedef struct {
     int32_t peak_bin, peak_mask, peak_offset;
     int32_t sig_start, sig_len, noise_start, noise_len; /* circular spectrum windows for computeSNR */
     int32_t demod_shift; /* the shift the demod stage used */
-    int32_t xchg_timeout;/* 1 = a peer's rows never arrived (pcs_enqueue_owner_tail) */
+    int32_t xchg_timeout;/* pcs_shard_*: bit 0 = a peer's rows or the chunk never arrived, bit 1 = a flag overran */
 } pcs_result;
 
 typedef struct pcs_handle pcs_handle;

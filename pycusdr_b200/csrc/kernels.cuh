@@ -1949,11 +1949,6 @@ __global__ void flags_set_kernel(FlagList f, unsigned long long value, unsigned 
         if (threadIdx.x == 0) *tagp = value + inc;
     }
 }
-__global__ void peer_flag_kernel(unsigned long long* flag, unsigned long long value) {
-    // the rows were stored by the preceding kernels of this stream; make them visible system-wide, then publish
-    __threadfence_system();
-    st_release_sys(flag, value);
-}
 
 // Lane i < n spins until flags[i * stride] >= want[i] (want 0 = nothing to wait for).  err (device word, may be null)
 // gets bit 0 on a timeout.  exact != 0: a flag beyond `want` sets bit 1 (overrun).  res (may be null): xchg_timeout.
