@@ -67,6 +67,16 @@ def _compare(dem, orc, x, exact_bits=True):
     # decisions may differ only where two candidates tie to within fp32-FFT rounding
     assert len(diff) <= max(2, 0.005 * len(orc.last["sym"])), (diff[:10], dem.last["sym"][diff[:10]], orc.last["sym"][diff[:10]],
                                                                orc.last["mag"][diff[:10]], dem.last["mag"][diff[:10]])
+    # ... and a tie it must be: where the decisions differ both implementations saw maxima of the same height (the reported
+    # magnitude is the larger candidate's |y|^2 in either case), to the 1e-4 the surface itself agrees to
+    if len(diff):
+        scale = float(np.max(orc.last["mag"]))
+        worst = float(np.max(np.abs(dem.last["mag"][diff].astype(np.float64) - orc.last["mag"][diff].astype(np.float64))))
+        print(f"[parity] {len(diff)} of {len(orc.last['sym'])} symbol decisions differ from the oracle's; |mag difference| there <= "
+              f"{worst / scale:.2e} of the largest magnitude")
+        assert worst <= 1e-4 * scale
+    else:
+        print(f"[parity] all {len(orc.last['sym'])} symbol decisions equal the oracle's")
     if exact_bits and same == 1.0:
         np.testing.assert_array_equal(ba[0], bb[0])
         # (the trust bytes are the raw low-order bytes of the float magnitudes, dem_base:1005-1007: they differ between
