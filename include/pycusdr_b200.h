@@ -210,6 +210,16 @@ int pcs_get_plan(const pcs_handle* h, pcs_plan_info* info);
 int pcs_factorise_bank(const float* masks /* complex64[M*nfft] */, int32_t nfft, int32_t num_masks, int32_t support_pos,
                        int32_t support_neg, const int32_t* shifts, int32_t num_shifts, int32_t log2_block, int32_t* seg_len,
                        int32_t* num_seg, int32_t* num_basis, int32_t* sel_out, float* coef_out, float* basis_spec_out);
+/* Which form of the factorised search a bank can take (host only, no GPU; the second plan-time step of pcs_create after
+ * pcs_factorise_bank).  *form = 1: general (selectors read at run time; sel / coef untouched).  2: a COMPLETE BINARY BANK --
+ * num_basis = 2 and the num_masks = 2^num_seg selector rows are all different (what an FSK-2 bank is): coef is rewritten in
+ * code order, code = sum_j sel[m][j] 2^j, and sel[0 .. M) becomes the table code -> mask, so that every selection in the
+ * kernel is static.  3: as 2, and (only looked for when allow_shared_sums != 0) the coefficient of segment j is the same
+ * for all codes with the same low j + 1 bits -- for FSK-2 the phase a symbol starts with is set by the symbols before it --
+ * so filters with the same prefix share their partial sums (2 + 4 + .. + 2^J complex multiply-adds per output instead of
+ * J 2^J).  sel: int32[M * J] in, int32[>= M] out; coef: complex64[D * M * J] in / out. */
+int pcs_bank_code_order(int32_t num_masks, int32_t num_seg, int32_t num_basis, int32_t num_shifts, int32_t* sel, float* coef,
+                        int32_t allow_shared_sums, int32_t* form);
 /* What the handle's search uses: out[0] = 0 unfactorised, 1 factorised (general form: selectors read at run time), 2 = a
  * complete binary bank (R = 2, the M = 2^J selector rows all different: static selection, combinations from registers), 3 = and
  * the coefficient of segment j depends on the selectors of segments 0..j only (partial sums shared between filters with

@@ -76,6 +76,7 @@ SYMBOLS = {
     "pcs_get_plan": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "pcs_factorise_bank": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P]),
+    "pcs_bank_code_order": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "pcs_get_bank_factor": (C.c_int, [_P, _P]),
     "pcs_launch_count": (C.c_int64, [_P]),
     "pcs_stream": (C.c_uint64, [_P]),
@@ -205,6 +206,19 @@ def factorise_bank(masks, support_pos, support_neg, shifts, log2_block):
     S, J, R = S.value, J.value, R.value
     return {"S": S, "J": J, "R": R, "sel": sel[:M * J].reshape(M, J).copy(),
             "coef": coef[:D * M * J].reshape(D, M, J).copy(), "basis_spec": spec[:D * R * B].reshape(D, R, B).copy()}
+
+
+def bank_code_order(fact, allow_shared_sums=True):
+    """Form of the factorised search a bank can take (``pcs_bank_code_order``; host only): returns ``(form, sel, coef)`` --
+    for form >= 2 ``coef`` is in code order and ``sel`` is the table code -> mask."""
+    sel = np.ascontiguousarray(fact["sel"], dtype=np.int32).copy()
+    coef = np.ascontiguousarray(fact["coef"], dtype=np.complex64).copy()
+    D, M, J = coef.shape
+    form = C.c_int32(0)
+    rc = load().pcs_bank_code_order(M, J, int(fact["R"]), D, _ptr(sel), _ptr(coef), int(bool(allow_shared_sums)), C.byref(form))
+    if rc != 0:
+        raise NativeError(rc, load().pcs_last_error().decode())
+    return form.value, (sel.reshape(-1)[:M].copy() if form.value >= 2 else sel), coef
 
 
 def fill_gaps(idx, min_gap, nfft):

@@ -233,3 +233,44 @@ int pcs_factorise_bank(const float* masks, int32_t nfft, int32_t num_masks, int3
         for (size_t q = 0; q < spec.size(); ++q) { basis_spec_out[2 * q] = (float)spec[q].real(); basis_spec_out[2 * q + 1] = (float)spec[q].imag(); }
     return PCS_OK;
 }
+
+// See include/pycusdr_b200.h.  Decides which form of search_fb_kernel a factorised bank can take and, for a complete binary
+// bank, puts the tables into the kernel's order.
+int pcs_bank_code_order(int32_t num_masks, int32_t num_seg, int32_t num_basis, int32_t num_shifts, int32_t* sel, float* coef,
+                        int32_t allow_shared_sums, int32_t* form) {
+    if (!sel || !coef || !form || num_masks < 1 || num_seg < 1 || num_seg > PCS_FB_MAX_SEG || num_basis < 1 || num_shifts < 1)
+        return pcs_fail_msg(PCS_ERR_INVALID, "pcs_bank_code_order: bad argument");
+    const int M = num_masks, J = num_seg, D = num_shifts;
+    *form = 1;
+    if (num_basis != 2 || J > 3 || M != (1 << J)) return PCS_OK;
+    std::vector<int32_t> code_mask((size_t)M, -1);
+    for (int m = 0; m < M; ++m) {
+        int code = 0;
+        for (int j = 0; j < J; ++j) {
+            const int r = sel[(size_t)m * J + j];
+            if (r < 0 || r > 1) return pcs_fail_msg(PCS_ERR_INVALID, "pcs_bank_code_order: selector outside the basis");
+            code |= r << j;
+        }
+        if (code_mask[code] >= 0) return PCS_OK;          // two filters with the same selectors: not complete
+        code_mask[code] = m;
+    }
+    std::vector<float> cc((size_t)2 * D * M * J);
+    for (int d = 0; d < D; ++d)
+        for (int code = 0; code < M; ++code)
+            for (int q = 0; q < 2 * J; ++q)
+                cc[2 * (((size_t)d * M + code) * J) + q] = coef[2 * (((size_t)d * M + code_mask[code]) * J) + q];
+    for (size_t q = 0; q < cc.size(); ++q) coef[q] = cc[q];
+    for (int code = 0; code < M; ++code) sel[code] = code_mask[code];
+    *form = 2;
+    if (!allow_shared_sums) return PCS_OK;
+    for (size_t d = 0; d < (size_t)D; ++d)
+        for (int code = 0; code < M; ++code)
+            for (int j = 0; j + 1 < J; ++j) {
+                const float* a = &coef[2 * ((d * M + code) * J + j)];
+                const float* b = &coef[2 * ((d * M + (code & ((2 << j) - 1))) * J + j)];
+                const float tol = 1e-6f * (fabsf(b[0]) + fabsf(b[1]));
+                if (fabsf(a[0] - b[0]) > tol || fabsf(a[1] - b[1]) > tol) return PCS_OK;
+            }
+    *form = 3;
+    return PCS_OK;
+}

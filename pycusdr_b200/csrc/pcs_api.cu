@@ -588,34 +588,10 @@ static int plan_overlap_save(pcs_handle* h, const float* masks_host) {
         CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device));
         if (fR > 0 && fb_smem_bytes(best, fR, M) <= (size_t)max_smem) {
             const size_t nb = ((size_t)h->D * fR) << best, nc = (size_t)h->D * M * fJ, ns = (size_t)M * fJ;
-            // complete binary bank: filters in code order (code = sum_j sel[m][j] 2^j), sel becomes code -> mask
-            std::vector<int32_t> code_mask((size_t)M, -1);
-            bool complete = fR == 2 && fJ <= 3 && M == (1 << fJ);
-            for (int m = 0; m < M && complete; ++m) {
-                int code = 0;
-                for (int j = 0; j < fJ; ++j) code |= sel[(size_t)m * fJ + j] << j;
-                if (code_mask[code] >= 0) complete = false;
-                code_mask[code] = m;
-            }
-            if (complete) {
-                std::vector<float> cc(coef.size());
-                for (int d = 0; d < h->D; ++d)
-                    for (int code = 0; code < M; ++code)
-                        memcpy(&cc[2 * (((size_t)d * M + code) * fJ)], &coef[2 * (((size_t)d * M + code_mask[code]) * fJ)], sizeof(float) * 2 * fJ);
-                coef.swap(cc);
-                std::copy(code_mask.begin(), code_mask.end(), sel.begin());
-            }
-            h->fb_complete = complete ? 1 : 0;
-            if (complete && h->cfg.reserved[0] & 4) complete = false;      // experiment knob: no shared partial sums
-            for (size_t d = 0; d < (size_t)h->D && complete; ++d)
-                for (int code = 0; code < M && complete; ++code)
-                    for (int j = 0; j + 1 < fJ; ++j) {
-                        const float* a = &coef[2 * ((d * M + code) * fJ + j)];
-                        const float* b = &coef[2 * ((d * M + (code & ((2 << j) - 1))) * fJ + j)];
-                        const float tol = 1e-6f * (fabsf(b[0]) + fabsf(b[1]));
-                        if (fabsf(a[0] - b[0]) > tol || fabsf(a[1] - b[1]) > tol) { complete = false; break; }
-                    }
-            if (complete) h->fb_complete = 2;
+            // which form of search_fb_kernel the bank can take; a complete binary bank gets its tables in code order
+            int32_t form = 1;
+            if (int rc = pcs_bank_code_order(M, fJ, fR, h->D, sel.data(), coef.data(), (h->cfg.reserved[0] & 4) ? 0 : 1, &form)) return rc;
+            h->fb_complete = form - 1;
             if (int rc = dev_alloc(h, &h->d_fb_basis, nb)) return rc;
             if (int rc = dev_alloc(h, &h->d_fb_coef, nc)) return rc;
             if (int rc = dev_alloc(h, &h->d_fb_sel, ns)) return rc;

@@ -88,3 +88,67 @@ def test_bad_geometry_is_rejected():
     masks = np.zeros((2, 1024), dtype=np.complex64)
     with pytest.raises(_native.NativeError):
         _native.factorise_bank(masks, 600, 600, np.zeros(2, np.int32), 10)       # support longer than the block
+
+
+def _incomplete_and_other_banks():
+    from pycusdr_b200.protocol.FSK2_base import fsk_phase_templates
+    N, sps = 2 ** 14, 128
+
+    def spectra(tmpl):
+        m = np.zeros((len(tmpl), N), dtype=np.complex128)
+        for i, tp in enumerate(tmpl):
+            m[i, :len(tp)] = tp
+        return np.conj(np.fft.fft(m, axis=1)).astype(np.complex64)
+    full = [np.array([(k >> 2) & 1, (k >> 1) & 1, k & 1]) for k in range(8)]
+    n = np.arange(sps)
+    tones = [np.exp(2j * np.pi * f * n / sps) for f in (-1.0, 0.5, 1.5)]
+    return N, {
+        "incomplete": spectra(fsk_phase_templates([p for k, p in enumerate(full) if k != 5], sps, 0.5)),
+        "three_tones": spectra([np.concatenate((tones[a], np.exp(0.3j * (a + 2 * b)) * tones[b])) for a in range(3) for b in range(3)]),
+        # complete, but the first segment's constant depends on the LAST symbol: no shared partial sums
+        "no_prefix": spectra([np.concatenate((np.exp(0.4j * b) * tones[a], tones[b])) for a in (0, 1) for b in (0, 1)]),
+    }
+
+
+def test_code_order_of_the_cc11xx_bank_and_shared_prefix_sums():
+    """pcs_bank_code_order: CC11xx is a complete binary bank whose coefficients depend on the code's prefix only (form 3).  The
+    combination the kernel then runs -- level j adds c[prefix][j] u_{bit j}[i + j S] to the partial sum of the prefix one bit
+    shorter -- must give the same y as the plain J-term sum in mask order."""
+    orc, masks, shifts = _bank("CC11xx.json", 14, 5)
+    lp, ln = _support(masks, masks.shape[1])
+    f = _native.factorise_bank(masks, lp, ln, shifts, 11)
+    form, code_mask, coef = _native.bank_code_order(f)
+    assert form == 3 and sorted(code_mask.tolist()) == list(range(8))
+    J, S = f["J"], f["S"]
+    for code, m in enumerate(code_mask):
+        assert [int(f["sel"][m, j]) for j in range(J)] == [(code >> j) & 1 for j in range(J)]
+        np.testing.assert_array_equal(coef[:, code, :], f["coef"][:, m, :])
+    form2, _, _ = _native.bank_code_order(f, allow_shared_sums=False)
+    assert form2 == 2
+    # the kernel's tree evaluation against the plain sum, on random u
+    rng = np.random.RandomState(3)
+    u = rng.randn(2, 1024) + 1j * rng.randn(2, 1024)
+    i = np.arange(512)
+    d = 2
+    for code, m in enumerate(code_mask):
+        plain = sum(f["coef"][d, m, j].astype(np.complex128) * u[f["sel"][m, j], i + j * S] for j in range(J))
+        part = 0
+        for j in range(J):
+            pre = code & ((2 << j) - 1)
+            part = part + coef[d, pre, j].astype(np.complex128) * u[(pre >> j) & 1, i + j * S]
+        assert np.max(np.abs(part - plain)) <= 1e-6 * np.max(np.abs(plain))
+
+
+def test_code_order_leaves_other_banks_in_the_general_form():
+    N, banks = _incomplete_and_other_banks()
+    shifts = (((np.arange(6) - 3) * 37) % N).astype(np.int32)
+    want = {"incomplete": 1, "three_tones": 1, "no_prefix": 2}
+    for name, masks in banks.items():
+        lp, ln = _support(masks, N)
+        f = _native.factorise_bank(masks, lp, ln, shifts, 11)
+        assert f is not None, name
+        form, sel, coef = _native.bank_code_order(f)
+        assert form == want[name], name
+        if form == 1:
+            np.testing.assert_array_equal(sel, f["sel"])
+            np.testing.assert_array_equal(coef, f["coef"])
