@@ -253,13 +253,14 @@ int pcs_enqueue_estimate_and_demod(pcs_handle* h, int32_t with_demod);
  *   - every rank searches its slice of the Doppler bins; the finishing CTAs of its search kernel store the slice's rows of
  *     the three [D][M] tables straight into the exchange region of the chunk's OWNER (seq % world) and raise a row flag.
  *   - the owner alone runs estimate + demodulation + timing + symbol decisions on the gathered tables (the very tables one
- *     GPU produces: results are bit-identical to pcs_process) and keeps the results in one of four result stages until
+ *     GPU produces: results are bit-identical to pcs_process) on one of four tail streams -- from an owned chunk's second
+ *     pass through a stage on as ONE CUDA graph launch -- and keeps the results in one of eight result stages until
  *     pcs_shard_fetch collects them.
- * pcs_shard_init allocates the exchange region (tables, flags, chunk ring of `ring` slots: even, <= 4 * world, 0 = choose)
+ * pcs_shard_init allocates the exchange region (tables, flags, chunk ring of `ring` slots: even, <= 8 * world, 0 = choose: 8)
  * and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles with any transport and passes them, in rank
  * order, to pcs_shard_attach.  pcs_shard_submit(seq) is then called on EVERY rank for seq = 0, 1, 2, ... (src is ignored
  * on ranks other than 0); it never blocks on another rank.  The owner must fetch chunk seq before it submits chunk
- * seq + 4 * world.  A handle initialised for sharding is dedicated to it.  world = 1 is allowed (a single GPU streaming
+ * seq + 8 * world.  A handle initialised for sharding is dedicated to it.  world = 1 is allowed (a single GPU streaming
  * through the same engine). */
 enum { PCS_SRC_DEVICE = 1, PCS_SRC_HOST = 2 };
 int pcs_shard_init(pcs_handle* h, int32_t rank, int32_t world, int32_t ring, void* ipc_handle_out /* 64 bytes */);
