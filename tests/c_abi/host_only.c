@@ -90,6 +90,35 @@ int main(void) {
     int hit = 0;
     for (int i = 0; i < found && i < 8; ++i) hit |= (at[i] - 8 + 1 == 30 && score[i] == 4);
     CHECK(hit);
+    /* plan-time bank factorisation (pcs_factorise_bank + pcs_bank_code_order): four filters = the 2 x 2 sequences of two
+     * 32-tap tones; spectra Mk[m][k] = conj(DFT_N(template))[k] by direct summation (N = 256) */
+    {
+        enum { N = 256, S = 32, M = 4, D = 3 };
+        static float masks[M][N][2];
+        const double tone[2] = {3.0, -5.0}, pi2 = 6.283185307179586;
+        for (int m = 0; m < M; ++m)
+            for (int k = 0; k < N; ++k) {
+                double re = 0, im = 0;
+                for (int n = 0; n < 2 * S; ++n) {
+                    const int seg = n / S, t = (m >> seg) & 1;
+                    const double ph = pi2 * tone[t] * (n % S) / S + (seg ? 0.7 * (m & 1) : 0.0) - pi2 * k * n / N;
+                    re += cos(ph); im += sin(ph);          /* template[n] exp(-2 pi i k n / N) */
+                }
+                masks[m][k][0] = (float)re; masks[m][k][1] = (float)-im;      /* conj */
+            }
+        const int32_t shifts[D] = {0, 5, 250};
+        int32_t seg = 0, nseg = 0, nbasis = 0, sel[M * PCS_FB_MAX_SEG], form = 0;
+        static float coef[2 * D * M * PCS_FB_MAX_SEG], spec[2 * D * PCS_FB_MAX_BASIS * 128];
+        /* taps of g = IFFT(Mk) sit at n = 0 and n = -63 .. -1: support_pos 0, support_neg 63 */
+        CHECK(pcs_factorise_bank(&masks[0][0][0], N, M, 0, 63, shifts, D, 7, &seg, &nseg, &nbasis, sel, coef, spec) == PCS_OK);
+        CHECK(seg == S && nseg == 2 && nbasis == 2);
+        CHECK(pcs_bank_code_order(M, nseg, nbasis, D, sel, coef, 1, &form) == PCS_OK);
+        CHECK(form == 3);                                   /* complete, and segment 0's constant depends on bit 0 only */
+        int seen = 0;
+        for (int c = 0; c < M; ++c) seen |= 1 << sel[c];
+        CHECK(seen == 15);
+        CHECK(pcs_factorise_bank(&masks[0][0][0], N, M, 200, 200, shifts, D, 7, &seg, &nseg, &nbasis, sel, coef, spec) != PCS_OK);
+    }
     printf("c abi host-only ok\n");
     return 0;
 }
