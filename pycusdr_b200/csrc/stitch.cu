@@ -120,12 +120,21 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
     std::vector<uint8_t>& bits = s->bits;
     long n_bits, n_err = 0;
     auto wrap = [M](int v) { return v < 0 ? v + M : v; };
-    for (int i = 0; i < n_sym; ++i)
-        if (sym[i] < -M || sym[i] >= M) return pcs_fail_msg(PCS_ERR_INVALID, "symbol index outside the look-up table");
+    {   // every index inside [-M, M) (NumPy's negative indices included): one branch-free pass
+        unsigned bad = 0;
+        for (int i = 0; i < n_sym; ++i) bad |= (unsigned)(sym[i] + M) >= (unsigned)(2 * M);
+        if (bad) return pcs_fail_msg(PCS_ERR_INVALID, "symbol index outside the look-up table");
+    }
     if (!s->bit_lut.empty()) {
         n_bits = n_sym;
         bits.resize(n_bits);
-        for (long i = 0; i < n_bits; ++i) bits[i] = s->bit_lut[wrap(sym[i])];           // dem_base:1020
+        uint8_t lut2[128];                                   // lut2[v + M] = bit_lut[v mod M] for v in [-M, M)
+        std::vector<uint8_t> big;
+        uint8_t* l2 = lut2;
+        if (2 * M > 128) { big.resize((size_t)2 * M); l2 = big.data(); }
+        for (int v = 0; v < M; ++v) l2[v] = l2[v + M] = s->bit_lut[v];
+        uint8_t* __restrict__ bo = bits.data();
+        for (long i = 0; i < n_bits; ++i) bo[i] = l2[sym[i] + M];                       // dem_base:1020
     } else {
         const int K = c.lut_k;
         n_bits = n_sym - 1;
@@ -146,8 +155,17 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
     long start = -1, end = -1;
     for (long i = 0; i < n_sym; ++i)
         if (centre[i] >= half) { start = i; break; }
-    for (long i = 0; i < n_sym; ++i)
-        if (centre[i] > c.nfft - half) { end = i; break; }
+    {   // first centre beyond nfft - half: near the END of the chunk, so look block by block (a max the compiler vectorises)
+        const int thr = c.nfft - half;
+        for (long i0 = 0; i0 < n_sym && end < 0; i0 += 256) {
+            const long i1 = std::min<long>(i0 + 256, n_sym);
+            int mx = INT32_MIN;
+            for (long i = i0; i < i1; ++i) mx = std::max(mx, centre[i]);
+            if (mx > thr)
+                for (long i = i0; i < i1; ++i)
+                    if (centre[i] > thr) { end = i; break; }
+        }
+    }
     if (start < 0 || end < 0)
         return pcs_fail_msg(PCS_ERR_STATE, "no symbol centre inside the overlap windows (the reference raises IndexError here)");
     const long oo = c.overlap_offset;
@@ -200,10 +218,12 @@ int pcs_stitch_chunk(pcs_stitcher* s, const int32_t* sym, const int32_t* centre,
     // the three arrays have the same length except in the NRZ-S path at the very end of the chunk; the reference then
     // fails on the boolean index -- here the shorter length is used
     const long n_ret = std::min(n_win, wc.len());
-    for (long i = 0; i < n_ret; ++i) {
-        bits_out[i] = b[w.lo + i];
-        centres_out[i] = (uint8_t)centre[wc.lo + i];
-        trust_out[i] = trust[wc.lo + i];
+    if (n_ret > 0) {
+        memcpy(bits_out, b + w.lo, (size_t)n_ret);
+        memcpy(trust_out, trust + wc.lo, (size_t)n_ret);
+        uint8_t* __restrict__ co = centres_out;
+        const int32_t* __restrict__ ci = centre + wc.lo;
+        for (long i = 0; i < n_ret; ++i) co[i] = (uint8_t)ci[i];                        // .astype(np.uint8), dem_base:859
     }
     if (n_clipped > 0) {
         const long N = c.nfft;
